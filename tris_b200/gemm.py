@@ -1,0 +1,187 @@
+"""Python front-end of the tcgen05 GEMM / implicit-conv kernel (tris_gemm in include/tris_sm100.h).
+
+All tensors are CUDA, contiguous; activations / weights bf16, bias / stats / weight gradients fp32.
+Layouts: linear x [M,K], w [N,K] (nn.Linear layout); conv activations NHWC, 3x3 weights packed [Cout, 9*Cin]
+with k = (r*3+s)*Cin + ci  (``pack_conv3x3``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+SMS = 148
+
+
+def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
+    """UMMA N per tile: the widest of 256/128/64 that still yields >= one wave of tiles (148 SMs)."""
+    if n <= 32 and not mn_major_b:
+        return 32
+    n_pad = ((n + 63) // 64) * 64
+    cands = [bn for bn in (256, 128, 64) if bn <= n_pad] or [64]
+    for bn in cands:
+        if tiles_m * ((n + bn - 1) // bn) >= SMS:
+            return bn
+    return cands[-1]
+
+
+def _desc(**kw) -> L.GemmDesc:
+    d = L.GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def _chk(t, dtype, name):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous CUDA {dtype}, got {t.dtype} {t.shape}"
+
+
+def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, stats=None,
+               block_n=None):
+    """out[M,N] = act(x[M,K] @ w[N,K]^T + bias) + residual ; optional column stats (sum, sumsq) into stats[2N]."""
+    _chk(x, torch.bfloat16, "x"); _chk(w, torch.bfloat16, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=out_dtype)
+    tiles_m = (m + 127) // 128
+    bn = block_n or _bn_for(n, tiles_m)
+    d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(out), bias=L.ptr(bias), residual=L.ptr(residual), stats=L.ptr(stats),
+              a_mode=L.OP_K2D, b_mode=L.OP_K2D, M=m, N=n, K=k, lda=k, ldb=k, ldd=n, taps=1, block_n=bn, split_k=1,
+              act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
+    L.gemm_raw(d)
+    return out
+
+
+def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None):
+    """dx[M,K] = dy[M,N] @ w[N,K]   (w read MN-major: no transposed weight copy)."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(w, torch.bfloat16, "w")
+    m, n = dy.shape
+    k = w.shape[1]
+    assert w.shape[0] == n
+    if out is None:
+        out = torch.empty((m, k), device=dy.device, dtype=out_dtype)
+    tiles_m = (m + 127) // 128
+    bn = block_n or _bn_for(k, tiles_m, True)
+    d = _desc(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), a_mode=L.OP_K2D, b_mode=L.OP_MN2D,
+              M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1,
+              out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
+    L.gemm_raw(d)
+    return out
+
+
+def _split_for(tiles: int, kblocks: int) -> int:
+    if tiles >= SMS:
+        return 1
+    s = (2 * SMS + tiles - 1) // tiles
+    return max(1, min(s, max(1, kblocks // 4)))
+
+
+def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
+    """dw[N,K] (f32) (+)= dy[M,N]^T @ x[M,K]  (both operands MN-major, contraction over rows, split-K)."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(x, torch.bfloat16, "x")
+    m, n = dy.shape
+    k = x.shape[1]
+    assert x.shape[0] == m
+    tiles_m = (n + 127) // 128
+    bn = block_n or _bn_for(k, tiles_m, True)
+    tiles = tiles_m * ((k + bn - 1) // bn)
+    kblocks = (m + 63) // 64
+    sk = split_k or _split_for(tiles, kblocks)
+    atomic = 1 if (sk > 1 or accumulate) else 0
+    if out is None:
+        out = (torch.zeros if atomic else torch.empty)((n, k), device=dy.device, dtype=torch.float32)
+    elif atomic and not accumulate:
+        out.zero_()
+    _chk(out, torch.float32, "out")
+    d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, M=n, N=k, K=m, lda=n, ldb=k,
+              ldd=k, taps=1, block_n=bn, split_k=sk, out_dtype=L.DT_F32, atomic=atomic)
+    L.gemm_raw(d)
+    return out
+
+
+# --------------------------------------------------------------------------------------- 3x3 convolution
+def pack_conv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32/bf16 -> bf16 [Cout, 9*Cin], k = (r*3+s)*Cin + ci."""
+    co, ci, kh, kw = w_oihw.shape
+    return w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+
+
+def unpack_conv3x3_grad(dwp: torch.Tensor, cin: int) -> torch.Tensor:
+    co = dwp.shape[0]
+    return dwp.reshape(co, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+
+
+def conv_tile(h: int, w: int, max_rows: int = 128, mult: int = 1):
+    """Spatial patch (th, tw) for one tile: maximise useful rows / covered rows."""
+    best, best_eff = None, -1.0
+    for tw in range(1, min(w, max_rows) + 1):
+        for th in range(1, min(h, max_rows // tw) + 1):
+            rows = th * tw
+            if rows % mult:
+                continue
+            cover = ((h + th - 1) // th) * th * ((w + tw - 1) // tw) * tw
+            eff = (h * w / cover) * (rows / max_rows)
+            if eff > best_eff + 1e-9 or (abs(eff - best_eff) < 1e-9 and tw > best[1]):
+                best, best_eff = (th, tw), eff
+    return best
+
+
+def conv3x3_fwd(x, wp, stats=None, out=None, block_n=None, taps=9):
+    """y[n,h,w,co] = conv3x3(x[n,h,w,ci], pad 1, stride 1); wp packed [co, taps*ci]. taps=1 -> 1x1 conv via TMA-4D."""
+    _chk(x, torch.bfloat16, "x"); _chk(wp, torch.bfloat16, "wp")
+    n, h, w, ci = x.shape
+    co = wp.shape[0]
+    assert wp.shape[1] == taps * ci and ci % 64 == 0
+    if out is None:
+        out = torch.empty((n, h, w, co), device=x.device, dtype=torch.bfloat16)
+    th, tw = conv_tile(h, w)
+    tiles_m = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
+    bn = block_n or _bn_for(co, tiles_m)
+    d = _desc(a=L.ptr(x), b=L.ptr(wp), d=L.ptr(out), stats=L.ptr(stats), a_mode=L.OP_CONV, b_mode=L.OP_K2D,
+              M=n * h * w, N=co, K=taps * ci, ldb=taps * ci, ldd=co, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw,
+              taps=taps, block_n=bn, split_k=1, out_dtype=L.DT_BF16)
+    L.gemm_raw(d)
+    return out
+
+
+def conv3x3_dgrad(dy, wp, cin, out=None, block_n=None):
+    """dx[n,h,w,ci] = conv_transpose3x3(dy[n,h,w,co]); wp is the forward packing [co, 9*ci] read MN-major."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(wp, torch.bfloat16, "wp")
+    n, h, w, co = dy.shape
+    assert wp.shape == (co, 9 * cin) and co % 64 == 0
+    if out is None:
+        out = torch.empty((n, h, w, cin), device=dy.device, dtype=torch.bfloat16)
+    th, tw = conv_tile(h, w)
+    tiles_m = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
+    bn = block_n or _bn_for(cin, tiles_m, True)
+    d = _desc(a=L.ptr(dy), b=L.ptr(wp), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_MN2D, M=n * h * w, N=cin,
+              K=9 * co, ldb=9 * cin, ldd=cin, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, flip=1,
+              b_tap_stride=cin, block_n=bn, split_k=1, out_dtype=L.DT_BF16)
+    L.gemm_raw(d)
+    return out
+
+
+def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
+    """dwp[co, 9*ci] (f32) = sum_pixels dy[.,co] * x[. + tap, ci]."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(x, torch.bfloat16, "x")
+    n, h, w, co = dy.shape
+    ci = x.shape[3]
+    assert x.shape[:3] == dy.shape[:3]
+    th, tw = conv_tile(h, w, max_rows=96, mult=16)
+    kblocks = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
+    tiles_m = (co + 127) // 128
+    bn = block_n or _bn_for(ci, 9 * tiles_m, True)
+    tiles = 9 * tiles_m * ((ci + bn - 1) // bn)
+    sk = split_k or _split_for(tiles, kblocks)
+    atomic = 1 if sk > 1 else 0
+    if out is None:
+        out = (torch.zeros if atomic else torch.empty)((co, 9 * ci), device=dy.device, dtype=torch.float32)
+    elif atomic:
+        out.zero_()
+    d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_CONV, M=co, N=ci, K=n * h * w,
+              ldd=9 * ci, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, wgrad=1, block_n=bn, split_k=sk,
+              out_dtype=L.DT_F32, atomic=atomic)
+    L.gemm_raw(d)
+    return out
