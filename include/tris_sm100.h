@@ -72,6 +72,9 @@ typedef struct tris_gemm_desc {
     int32_t out_dtype;    /* TRIS_DT_* */
     int32_t atomic;       /* 1 = red.add.f32 into d (d pre-zeroed by the caller) */
     int32_t max_ctas;     /* 0 = one per SM */
+    void* d_pre;          /* optional bf16 [M, ldd]: pre-activation (post-bias) values, saved for backward */
+    const void* dact_src; /* optional bf16 [M, ldd]: epilogue multiplies by act'(dact_src) instead of applying act
+                             (fuses the QuickGELU / ReLU derivative into a dgrad GEMM) */
 } tris_gemm_desc;
 
 int tris_gemm(const tris_gemm_desc* desc, tris_stream_t stream);

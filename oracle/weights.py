@@ -103,6 +103,11 @@ def make_rn50_clip_state_dict(seed: int = 0, prefix: str = "", embed_dim: int = 
             _conv(sd, p + "conv1.weight", planes, inplanes, 1, g); _bn(sd, p + "bn1", planes, g)
             _conv(sd, p + "conv2.weight", planes, planes, 3, g); _bn(sd, p + "bn2", planes, g)
             _conv(sd, p + "conv3.weight", planes * 4, planes, 1, g); _bn(sd, p + "bn3", planes * 4, g)
+            # residual-branch gain: small but non-zero.  gamma ~ U(0.5,1.5) on every branch makes a random-init
+            # train-mode BN ResNet chaotic (perturbations grow ~1.3x per block: bf16 storage noise of 1% becomes
+            # 50% at c4 even in the fp32 reference), which says nothing about kernel correctness; the reference's
+            # own init uses gamma = 0 here (model.py:520-523), trained checkpoints sit in between.
+            sd[p + "bn3.weight"] = _uniform(g, (planes * 4,), 0.1, 0.3)
             if stride > 1 or inplanes != planes * 4:
                 _conv(sd, p + "downsample.0.weight", planes * 4, inplanes, 1, g)
                 _bn(sd, p + "downsample.1", planes * 4, g)

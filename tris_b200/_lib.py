@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("taps", C.c_int32), ("flip", C.c_int32), ("wgrad", C.c_int32), ("b_tap_stride", C.c_int32),
         ("block_n", C.c_int32), ("split_k", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32),
         ("atomic", C.c_int32), ("max_ctas", C.c_int32),
+        ("d_pre", C.c_void_p), ("dact_src", C.c_void_p),
     ]
 
 

@@ -35,6 +35,8 @@ struct KParams {
     const float* bias;
     const __nv_bfloat16* residual;
     float* stats;
+    __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
+    const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
     int ldd, act, out_f32, atomic;
 };
 
@@ -68,6 +70,15 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
         c.n_i = r / p.tiles_h;
     }
     return c;
+}
+
+__device__ __forceinline__ float act_grad(float p, int act) {
+    if (act == TRIS_ACT_RELU) return p > 0.f ? 1.f : 0.f;
+    if (act == TRIS_ACT_QUICKGELU) {
+        const float sg = 1.f / (1.f + __expf(-1.702f * p));
+        return sg * (1.f + 1.702f * p * (1.f - sg));
+    }
+    return 1.f;
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -280,13 +291,41 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         atomicAdd(p.stats + p.N + ncol0 + lane, c2);
                     }
                 }
-                if (p.act != TRIS_ACT_NONE) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
-                }
                 // per-thread predicate from here on: no warp-collective ops inside (tcgen05.ld is .sync.aligned)
                 if (rvalid) {
                 const long off = grow * p.ldd + col_base + ch * 32;
+                if (p.d_pre != nullptr) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (ncol0 + g * 8 < p.N) {
+                            uint4 o;
+                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                o2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                            reinterpret_cast<uint4*>(p.d_pre + off)[g] = o;
+                        }
+                    }
+                }
+                if (p.dact_src != nullptr) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(p.dact_src + off);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (ncol0 + g * 8 < p.N) {
+                            uint4 rr = __ldg(sp + g);
+                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = __bfloat1622float2(r2[j]);
+                                v[g * 8 + 2 * j] *= act_grad(f.x, p.act);
+                                v[g * 8 + 2 * j + 1] *= act_grad(f.y, p.act);
+                            }
+                        }
+                    }
+                } else if (p.act != TRIS_ACT_NONE) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
+                }
                 if (p.residual != nullptr) {
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
@@ -428,6 +467,8 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
 
     p.idesc = ptx::umma_idesc(1u, a_mn ? 1u : 0u, b_mn ? 1u : 0u, kBlockM, bn);
     p.d = g->d; p.bias = g->bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual); p.stats = g->stats;
+    p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
+    p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;
 
     // ---- tensor maps

@@ -1,0 +1,439 @@
+// Non-GEMM pieces of the CLIP transformer blocks (text towers, width 512 / 8 heads / L=20 causal; aux ViT-B/32,
+// width 768 / 12 heads / L=50): token embedding, LayerNorm fwd/bwd, small-sequence multi-head attention fwd/bwd held
+// entirely in shared memory, row gather / scatter-add, column sums (bias gradients).
+//
+// Replaces nn.Embedding + positional add (CLIP/clip/model.py:553-554), LayerNorm (:352-358), nn.MultiheadAttention's
+// softmax(QK^T/sqrt(d)+mask)V (:369,381) and the EOT gather (:562) of the reference; the linears run in gemm_sm100.cu.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------- embedding
+// one block per sentence: x[n,l,:] = E[ids[n,l]] + P[l]; eot[n] = n*L + argmax_l ids[n,l] (first maximum)
+__global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ E, const float* __restrict__ P,
+                                 __nv_bfloat16* __restrict__ x, int* __restrict__ eot, int L, int D) {
+    const int n = blockIdx.x;
+    if (threadIdx.x == 0 && eot != nullptr) {
+        int best = 0, bv = ids[n * L];
+        for (int l = 1; l < L; ++l) {
+            const int v = ids[n * L + l];
+            if (v > bv) { bv = v; best = l; }
+        }
+        eot[n] = n * L + best;
+    }
+    for (int i = threadIdx.x; i < L * D / 4; i += blockDim.x) {
+        const int l = (i * 4) / D, d = (i * 4) % D;
+        const int tok = ids[n * L + l];
+        const float4 e = __ldg(reinterpret_cast<const float4*>(E + static_cast<long>(tok) * D + d));
+        const float4 p = __ldg(reinterpret_cast<const float4*>(P + l * D + d));
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(x + (static_cast<long>(n) * L + l) * D + d);
+        o[0] = __floats2bfloat162_rn(e.x + p.x, e.y + p.y);
+        o[1] = __floats2bfloat162_rn(e.z + p.z, e.w + p.w);
+    }
+}
+
+// dE[ids] += dx ; dP[l] += sum_n dx   (fp32 atomics into the flat gradient buffer)
+__global__ void embed_bwd_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ dx, float* __restrict__ dE,
+                                 float* __restrict__ dP, int L, int D) {
+    const int n = blockIdx.x;
+    for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
+        const int l = i / D, d = i % D;
+        const float g = __bfloat162float(dx[(static_cast<long>(n) * L + l) * D + d]);
+        atomicAdd(dE + static_cast<long>(ids[n * L + l]) * D + d, g);
+        atomicAdd(dP + l * D + d, g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm (one warp per row)
+template <int MAXV>  // D <= MAXV * 32 * 8 ... we keep per-lane values in registers: D/32 floats per lane
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int rows, int D, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __nv_bfloat16* xr = x + static_cast<long>(row) * D;
+    float v[MAXV];
+    float s = 0.f;
+    const int per = D / 32;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (i < per) {
+            v[i] = __bfloat162float(xr[i * 32 + lane]);
+            s += v[i];
+        }
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < per) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    __nv_bfloat16* yr = y + static_cast<long>(row) * D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < per) {
+            const int c = i * 32 + lane;
+            yr[c] = __float2bfloat16((v[i] - mean) * rstd * gamma[c] + beta[c]);
+        }
+    if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dx = (add ? add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ add,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows, int D) {
+    extern __shared__ float sm[];   // [2*D] block partials of dgamma/dbeta
+    const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = D / 32;
+    const bool want_param = dgamma != nullptr;
+    if (want_param) {
+        for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+    }
+    float pg[MAXV], pb[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) pg[i] = pb[i] = 0.f;
+    for (int row = blockIdx.x * warps + wid; row < rows; row += gridDim.x * warps) {
+        const long base = static_cast<long>(row) * D;
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[MAXV], xh[MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < per) {
+                const int c = i * 32 + lane;
+                const float d = __bfloat162float(dy[base + c]);
+                xh[i] = (__bfloat162float(x[base + c]) - mean) * rstd;
+                g[i] = d * gamma[c];
+                s1 += g[i];
+                s2 += g[i] * xh[i];
+                pg[i] += d * xh[i];
+                pb[i] += d;
+            }
+        s1 = warp_sum(s1) / D;
+        s2 = warp_sum(s2) / D;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < per) {
+                const int c = i * 32 + lane;
+                float o = rstd * (g[i] - s1 - xh[i] * s2);
+                if (add != nullptr) o += __bfloat162float(add[base + c]);
+                dx[base + c] = __float2bfloat16(o);
+            }
+    }
+    if (want_param) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < per) {
+                atomicAdd(&sm[i * 32 + lane], pg[i]);
+                atomicAdd(&sm[D + i * 32 + lane], pb[i]);
+            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            atomicAdd(dgamma + i, sm[i]);
+            atomicAdd(dbeta + i, sm[D + i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- attention (L <= 64, head dim 64)
+constexpr int HD = 64;
+constexpr int HDP = HD + 1;
+
+// one block (128 threads) per (sequence, head).  qkv: [N*L, 3*D] bf16 (q | k | v), out: [N*L, D]
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                       int L, int heads, int causal) {
+    extern __shared__ float sm[];
+    float* q = sm;
+    float* k = q + L * HDP;
+    float* v = k + L * HDP;
+    float* s = v + L * HDP;   // [L][L+1]
+    const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int D = heads * HD;
+    const long row0 = static_cast<long>(n) * L;
+    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+        const int l = i / HD, d = i % HD;
+        const __nv_bfloat16* r = qkv + (row0 + l) * 3 * D + h * HD + d;
+        q[l * HDP + d] = __bfloat162float(r[0]) * 0.125f;   // 1/sqrt(64)
+        k[l * HDP + d] = __bfloat162float(r[D]);
+        v[l * HDP + d] = __bfloat162float(r[2 * D]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
+        const int a = i / L, b = i % L;
+        float acc = -CUDART_INF_F;
+        if (!causal || b <= a) {
+            acc = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < HD; ++d) acc += q[a * HDP + d] * k[b * HDP + d];
+        }
+        s[a * (L + 1) + b] = acc;
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = wid; a < L; a += 4) {
+        float m = -CUDART_INF_F;
+        for (int b = lane; b < L; b += 32) m = fmaxf(m, s[a * (L + 1) + b]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int b = lane; b < L; b += 32) {
+            const float e = __expf(s[a * (L + 1) + b] - m);
+            s[a * (L + 1) + b] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        for (int b = lane; b < L; b += 32) s[a * (L + 1) + b] *= inv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+        const int a = i / HD, d = i % HD;
+        float acc = 0.f;
+        for (int b = 0; b < L; ++b) acc += s[a * (L + 1) + b] * v[b * HDP + d];
+        out[(row0 + a) * D + h * HD + d] = __float2bfloat16(acc);
+    }
+}
+
+// dqkv from dout, recomputing the probabilities.
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                       __nv_bfloat16* __restrict__ dqkv, int L, int heads, int causal) {
+    extern __shared__ float sm[];
+    float* q = sm;
+    float* k = q + L * HDP;
+    float* v = k + L * HDP;
+    float* go = v + L * HDP;
+    float* s = go + L * HDP;          // P  [L][L+1]
+    float* ds = s + L * (L + 1);      // dS [L][L+1]
+    const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int D = heads * HD;
+    const long row0 = static_cast<long>(n) * L;
+    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+        const int l = i / HD, d = i % HD;
+        const __nv_bfloat16* r = qkv + (row0 + l) * 3 * D + h * HD + d;
+        q[l * HDP + d] = __bfloat162float(r[0]) * 0.125f;
+        k[l * HDP + d] = __bfloat162float(r[D]);
+        v[l * HDP + d] = __bfloat162float(r[2 * D]);
+        go[l * HDP + d] = __bfloat162float(dout[(row0 + l) * D + h * HD + d]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
+        const int a = i / L, b = i % L;
+        float acc = -CUDART_INF_F, dp = 0.f;
+        if (!causal || b <= a) {
+            acc = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < HD; ++d) {
+                acc += q[a * HDP + d] * k[b * HDP + d];
+                dp += go[a * HDP + d] * v[b * HDP + d];
+            }
+        }
+        s[a * (L + 1) + b] = acc;
+        ds[a * (L + 1) + b] = dp;
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = wid; a < L; a += 4) {
+        float m = -CUDART_INF_F;
+        for (int b = lane; b < L; b += 32) m = fmaxf(m, s[a * (L + 1) + b]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int b = lane; b < L; b += 32) {
+            const float e = __expf(s[a * (L + 1) + b] - m);
+            s[a * (L + 1) + b] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        float delta = 0.f;
+        for (int b = lane; b < L; b += 32) {
+            const float p = s[a * (L + 1) + b] * inv;
+            s[a * (L + 1) + b] = p;
+            delta += p * ds[a * (L + 1) + b];
+        }
+        delta = warp_sum(delta);
+        for (int b = lane; b < L; b += 32) ds[a * (L + 1) + b] = s[a * (L + 1) + b] * (ds[a * (L + 1) + b] - delta);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+        const int a = i / HD, d = i % HD;
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int b = 0; b < L; ++b) {
+            dq += ds[a * (L + 1) + b] * k[b * HDP + d];
+            dk += ds[b * (L + 1) + a] * q[b * HDP + d];   // q already carries the 1/8 scale
+            dv += s[b * (L + 1) + a] * go[b * HDP + d];
+        }
+        __nv_bfloat16* r = dqkv + (row0 + a) * 3 * D + h * HD + d;
+        r[0] = __float2bfloat16(dq * 0.125f);
+        r[D] = __float2bfloat16(dk);
+        r[2 * D] = __float2bfloat16(dv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- gather / scatter / colsum
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                   int rows, int D) {
+    const int vecs = D >> 3;
+    for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < static_cast<long>(rows) * vecs;
+         v += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(v / vecs), c = static_cast<int>(v % vecs);
+        reinterpret_cast<uint4*>(out)[v] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long>(idx[r]) * D) + c);
+    }
+}
+// out (pre-zeroed by this kernel's first phase is not possible) -> caller zeroes; out[idx[r]] = src[r] (unique idx)
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                    int rows, int D) {
+    const int vecs = D >> 3;
+    for (long v = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; v < static_cast<long>(rows) * vecs;
+         v += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(v / vecs), c = static_cast<int>(v % vecs);
+        reinterpret_cast<uint4*>(out + static_cast<long>(idx[r]) * D)[c] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    }
+}
+
+// out[c] += sum_r x[r, c]   (x bf16 [rows, N]); grid = (ceil(N/64), row_chunks), block = (64, 4)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int rows, int N) {
+    __shared__ float part[4][64];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    float s = 0.f;
+    if (c < N)
+        for (int r = blockIdx.y * 4 + threadIdx.y; r < rows; r += gridDim.y * 4) s += __bfloat162float(x[static_cast<long>(r) * N + c]);
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) atomicAdd(out + c, part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]);
+}
+
+// ViT token assembly: tok[n,0,:] = cls + pos[0]; tok[n,1+p,:] = patch[n*P+p,:] + pos[1+p]
+__global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                    __nv_bfloat16* __restrict__ tok, int N, int T, int D) {
+    const long total = static_cast<long>(N) * T * D;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(i % D);
+        const long r = i / D;
+        const int t = static_cast<int>(r % T);
+        const long n = r / T;
+        const float base = (t == 0) ? cls[d] : __bfloat162float(patch[(n * (T - 1) + (t - 1)) * D + d]);
+        tok[i] = __float2bfloat16(base + pos[t * D + d]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D, tris_stream_t stream) {
+    if (D % 4) return tris::fail(TRIS_ERR_SHAPE, "tris_embed_fwd: D %% 4");
+    embed_fwd_kernel<<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, E, P, reinterpret_cast<__nv_bfloat16*>(x), eot, L, D);
+    TRIS_LAUNCH_OK("embed_fwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, int L, int D, tris_stream_t stream) {
+    embed_bwd_kernel<<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, reinterpret_cast<const __nv_bfloat16*>(dx), dE, dP, L, D);
+    TRIS_LAUNCH_OK("embed_bwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int rows, int D,
+                       float eps, tris_stream_t stream) {
+    if (D % 32 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_fwd: D=%d must be %%32 and <= 1024", D);
+    const int warps = 8;
+    layernorm_fwd_kernel<32><<<(rows + warps - 1) / warps, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, rows, D, eps);
+    TRIS_LAUNCH_OK("layernorm_fwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* add,
+                       void* dx, float* dgamma, float* dbeta, int rows, int D, tris_stream_t stream) {
+    if (D % 32 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: D=%d must be %%32 and <= 1024", D);
+    const int warps = 8;
+    int grid = (rows + warps - 1) / warps;
+    const int cap = 2 * tris::sm_count();
+    if (grid > cap) grid = cap;
+    layernorm_bwd_kernel<32><<<grid, warps * 32, 2 * D * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+        reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, D);
+    TRIS_LAUNCH_OK("layernorm_bwd_kernel");
+    return TRIS_OK;
+}
+
+static size_t attn_smem(int L, bool bwd) {
+    return static_cast<size_t>((bwd ? 4 : 3) * L * HDP + (bwd ? 2 : 1) * L * (L + 1)) * sizeof(float);
+}
+
+int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causal, tris_stream_t stream) {
+    if (L > 64 || L < 1) return tris::fail(TRIS_ERR_SHAPE, "tris_attn_fwd: L=%d must be in 1..64", L);
+    static bool attr = false;
+    if (!attr) { TRIS_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+    attn_fwd_kernel<<<n * heads, 128, attn_smem(L, false), reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), L, heads, causal);
+    TRIS_LAUNCH_OK("attn_fwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_attn_bwd(const void* qkv, const void* dout, void* dqkv, int n, int L, int heads, int causal, tris_stream_t stream) {
+    if (L > 64 || L < 1) return tris::fail(TRIS_ERR_SHAPE, "tris_attn_bwd: L=%d must be in 1..64", L);
+    static bool attr = false;
+    if (!attr) { TRIS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); attr = true; }
+    attn_bwd_kernel<<<n * heads, 128, attn_smem(L, true), reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout),
+        reinterpret_cast<__nv_bfloat16*>(dqkv), L, heads, causal);
+    TRIS_LAUNCH_OK("attn_bwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_gather_rows(const void* x, const int* idx, void* out, int rows, int D, tris_stream_t stream) {
+    if (D % 8) return tris::fail(TRIS_ERR_SHAPE, "tris_gather_rows: D %% 8");
+    const long total = static_cast<long>(rows) * (D / 8);
+    gather_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), idx, reinterpret_cast<__nv_bfloat16*>(out), rows, D);
+    TRIS_LAUNCH_OK("gather_rows_kernel");
+    return TRIS_OK;
+}
+
+int tris_scatter_rows(const void* src, const int* idx, void* out, int rows, int D, tris_stream_t stream) {
+    if (D % 8) return tris::fail(TRIS_ERR_SHAPE, "tris_scatter_rows: D %% 8");
+    const long total = static_cast<long>(rows) * (D / 8);
+    scatter_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), idx, reinterpret_cast<__nv_bfloat16*>(out), rows, D);
+    TRIS_LAUNCH_OK("scatter_rows_kernel");
+    return TRIS_OK;
+}
+
+int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream) {
+    dim3 grid((N + 63) / 64, rows >= 2048 ? 32 : (rows >= 256 ? 8 : 1));
+    colsum_kernel<<<grid, dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, N);
+    TRIS_LAUNCH_OK("colsum_kernel");
+    return TRIS_OK;
+}
+
+int tris_vit_assemble(const void* patch, const float* cls, const float* pos, void* tok, int n, int T, int D, tris_stream_t stream) {
+    const long total = static_cast<long>(n) * T * D;
+    int grid = static_cast<int>((total + 255) / 256);
+    if (grid > 8 * tris::sm_count()) grid = 8 * tris::sm_count();
+    vit_assemble_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(patch), cls, pos, reinterpret_cast<__nv_bfloat16*>(tok), n, T, D);
+    TRIS_LAUNCH_OK("vit_assemble_kernel");
+    return TRIS_OK;
+}
+
+}  // extern "C"

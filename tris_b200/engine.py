@@ -1,0 +1,191 @@
+"""Execution engines: bind a module tree (spec.build_tree) to a ParamStore + kernel towers, and expose them to
+torch.autograd as tower-level Functions with hand-written backward passes.
+
+Gradient convention: tower backward passes write parameter gradients straight into ``store.grad`` (views published
+as ``param.grad``); autograd only carries activation gradients between towers.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .resnet import ResNetTower
+from .store import ParamStore
+from .transformer import TextTower, VitTower
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _EngineBase:
+    def __init__(self, module, device, group_of, adjacent=()):
+        L.require_device()
+        self.module = module
+        self.store = ParamStore(module, device, group_of, adjacent)
+        self.anchor = torch.zeros(1, device=device, requires_grad=True)
+        self.fwd_id = 0
+        self.last_bwd_id = -1
+        self._seen_versions = None
+        self.extra_grad_keys = []
+
+    # ---- shadow maintenance
+    def _versions(self):
+        return sum(p._version for p in self.store.params.values())
+
+    def ensure_fresh(self, force=False):
+        v = self._versions()
+        if force or v != self._seen_versions or not self.store.shadow_valid:
+            with torch.no_grad():
+                self.store.refresh_shadow()
+                self.refresh_derived()
+            self._seen_versions = self._versions()
+
+    def refresh_derived(self):
+        pass
+
+    # ---- gradient buffer protocol (see ParamStore)
+    def begin_backward(self, fwd_id):
+        if self.last_bwd_id == fwd_id:
+            return
+        self.last_bwd_id = fwd_id
+        st = self.store
+        if st.params[st.trainable[0]].grad is None:
+            st.grad.zero_()
+        st.publish_grads()
+        for k in self.extra_grad_keys:
+            if st.params[k].grad is None:
+                st.params[k].grad = st.g(k)
+
+
+# ============================================================================================ aux CLIP (ViT-B/32 or RN)
+class _VitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, patches, eng, n):
+        need = patches.requires_grad
+        feat, rec = eng.vit.forward(patches, n, save=need)
+        ctx.eng, ctx.rec = eng, rec
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        return ctx.eng.vit.backward(ctx.rec, dfeat.contiguous()), None, None
+
+
+def patchify(img, ps=32):
+    """[N,3,H,W] -> bf16 [N*(H/ps)*(W/ps), 3*ps*ps] with k = c*ps*ps + py*ps + px (conv1.weight.reshape(W,-1) order)."""
+    n, c, h, w = img.shape
+    gh, gw = h // ps, w // ps
+    return img.reshape(n, c, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5).reshape(n * gh * gw, c * ps * ps).to(bf16).contiguous()
+
+
+class ClipEngine(_EngineBase):
+    """Standalone CLIPModel (the frozen auxiliary scorer): no gradient buffers are published."""
+
+    def __init__(self, module, device):
+        super().__init__(module, device, group_of=lambda k: 2)
+        self.text = TextTower(self.store, "")
+        if module.is_vit:
+            self.vit = VitTower(self.store)
+        else:
+            from .spec import RN_LAYERS
+            self.resnet = ResNetTower(self.store, module, "visual.", RN_LAYERS[module.kind])
+
+    def refresh_derived(self):
+        if not self.module.is_vit:
+            self.resnet.refresh()
+
+    def encode_image(self, image):
+        self.ensure_fresh()
+        if self.module.is_vit:
+            n = image.shape[0]
+            patches = patchify(image)
+            return _VitFn.apply(patches, self, n).float()
+        with torch.no_grad():
+            c4, _ = self.resnet.forward(image.float(), train=False)
+        return c4.permute(0, 3, 1, 2).float()
+
+    def encode_text(self, text):
+        self.ensure_fresh()
+        with torch.no_grad():
+            hidden, _, seq = self.text.forward(text, save=False, full_sequence=True)
+        return seq.float(), hidden.float()
+
+    def encode_text_hidden(self, text):
+        self.ensure_fresh()
+        with torch.no_grad():
+            return self.text.forward(text, save=False)[0]
+
+
+# ============================================================================================ TRIS Stage-1
+def _tris_group(key: str) -> int:
+    if key.startswith("backbone."):
+        if key.startswith("backbone.visual.attnpool.") or key == "backbone.logit_scale":
+            return 2
+        return 0
+    if key.startswith(("vis_project.", "lan_project.", "attn_fusion.")):
+        return 1
+    return 2
+
+
+_ADJ = [[f"attn_fusion.v_proj{i}.0.weight" for i in (1, 2, 3)], [f"attn_fusion.v_proj{i}.0.bias" for i in (1, 2, 3)],
+        [f"attn_fusion.v_proj{i}.1.weight" for i in (1, 2, 3)], [f"attn_fusion.v_proj{i}.1.bias" for i in (1, 2, 3)],
+        [f"attn_fusion.t_proj{i}.0.weight" for i in (1, 2, 3)], [f"attn_fusion.t_proj{i}.0.bias" for i in (1, 2, 3)]]
+
+
+class _ResNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, img, eng):
+        c4, tape = eng.resnet.forward(img, train=True)
+        ctx.eng, ctx.tape, ctx.fid = eng, tape, eng.fwd_id
+        return c4
+
+    @staticmethod
+    def backward(ctx, dc4):
+        ctx.eng.begin_backward(ctx.fid)
+        ctx.eng.resnet.backward(ctx.tape, dc4.contiguous())
+        ctx.tape = None
+        return None, None, None
+
+
+class _TextFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, ids, eng):
+        hidden, rec, _ = eng.text.forward(ids, save=True)
+        ctx.eng, ctx.rec, ctx.fid = eng, rec, eng.fwd_id
+        return hidden
+
+    @staticmethod
+    def backward(ctx, dh):
+        ctx.eng.begin_backward(ctx.fid)
+        ctx.eng.text.backward(ctx.rec, dh.contiguous())
+        ctx.rec = None
+        return None, None, None
+
+
+class Stage1Engine(_EngineBase):
+    def __init__(self, model, device):
+        adj = _ADJ if hasattr(model, "attn_fusion") else ()
+        super().__init__(model, device, _tris_group, adj)
+        from .spec import RN_LAYERS
+        self.resnet = ResNetTower(self.store, model, "backbone.visual.", RN_LAYERS[model.backbone.kind])
+        self.text = TextTower(self.store, "backbone.")
+        self.extra_grad_keys = ["logit_scale"]
+        from .head import Stage1Head
+        self.head = Stage1Head(self, model)
+
+    def refresh_derived(self):
+        self.resnet.refresh()
+
+    def towers(self, x, word_id, train: bool):
+        """-> (c4 bf16 NHWC, hidden bf16 [T, E]) with autograd edges when training under grad mode."""
+        self.ensure_fresh(force=train)
+        x = x.float()
+        if train and torch.is_grad_enabled():
+            self.fwd_id += 1
+            c4 = _ResNetFn.apply(self.anchor, x, self)
+            hidden = _TextFn.apply(self.anchor, word_id, self)
+        else:
+            with torch.no_grad():
+                c4, _ = self.resnet.forward(x, train=train)
+                hidden = self.text.forward(word_id, save=False)[0]
+        return c4, hidden

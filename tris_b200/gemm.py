@@ -37,7 +37,7 @@ def _chk(t, dtype, name):
 
 
 def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dtype=torch.bfloat16, stats=None,
-               block_n=None):
+               block_n=None, d_pre=None):
     """out[M,N] = act(x[M,K] @ w[N,K]^T + bias) + residual ; optional column stats (sum, sumsq) into stats[2N]."""
     _chk(x, torch.bfloat16, "x"); _chk(w, torch.bfloat16, "w")
     m, k = x.shape
@@ -49,12 +49,13 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
     bn = block_n or _bn_for(n, tiles_m)
     d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(out), bias=L.ptr(bias), residual=L.ptr(residual), stats=L.ptr(stats),
               a_mode=L.OP_K2D, b_mode=L.OP_K2D, M=m, N=n, K=k, lda=k, ldb=k, ldd=n, taps=1, block_n=bn, split_k=1,
-              act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
+              act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16, d_pre=L.ptr(d_pre))
     L.gemm_raw(d)
     return out
 
 
-def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None):
+def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None, dact_src=None,
+                 act=L.ACT_NONE, bias=None):
     """dx[M,K] = dy[M,N] @ w[N,K]   (w read MN-major: no transposed weight copy)."""
     _chk(dy, torch.bfloat16, "dy"); _chk(w, torch.bfloat16, "w")
     m, n = dy.shape
@@ -64,9 +65,9 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
         out = torch.empty((m, k), device=dy.device, dtype=out_dtype)
     tiles_m = (m + 127) // 128
     bn = block_n or _bn_for(k, tiles_m, True)
-    d = _desc(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), a_mode=L.OP_K2D, b_mode=L.OP_MN2D,
-              M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1,
-              out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
+    d = _desc(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
+              b_mode=L.OP_MN2D, M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1, act=act,
+              dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
     L.gemm_raw(d)
     return out
 

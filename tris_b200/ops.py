@@ -1,0 +1,202 @@
+"""Tensor-level wrappers of the non-GEMM kernels of libtris_sm100.so (see include/tris_sm100.h).
+
+Every function takes contiguous CUDA tensors, launches on torch's current stream and returns torch tensors.
+No torch arithmetic happens here; missing library / wrong device raises (``_lib``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+bf16, f32 = torch.bfloat16, torch.float32
+P = L.ptr
+
+
+def _vp(t):
+    return C.c_void_p(P(t))
+
+
+def empty(shape, like, dtype=bf16):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+# ------------------------------------------------------------------ BatchNorm family (NHWC)
+class BNState:
+    """Per-layer BatchNorm tensors handed to the kernels (all fp32 [C])."""
+    __slots__ = ("gamma", "beta", "rm", "rv", "mean", "invstd", "dgamma", "dbeta")
+
+    def __init__(self, gamma, beta, rm, rv, dgamma=None, dbeta=None):
+        self.gamma, self.beta, self.rm, self.rv = gamma, beta, rm, rv
+        self.mean = torch.empty_like(gamma)
+        self.invstd = torch.empty_like(gamma)
+        self.dgamma, self.dbeta = dgamma, dbeta
+
+
+def bn_apply(y, stats, bn: BNState, train, relu=True, pool=1, y1=None, stats1=None, bn1: BNState = None, residual=None,
+             momentum=0.1, eps=1e-5):
+    n, h, w, c = y.shape
+    out = empty((n, h // pool, w // pool, c), y)
+    L.call("tris_bn_apply_fwd", _vp(y), _vp(stats), _vp(bn.gamma), _vp(bn.beta), _vp(bn.rm), _vp(bn.rv), _vp(bn.mean),
+           _vp(bn.invstd), _vp(y1), _vp(stats1), _vp(bn1.gamma if bn1 else None), _vp(bn1.beta if bn1 else None),
+           _vp(bn1.rm if bn1 else None), _vp(bn1.rv if bn1 else None), _vp(bn1.mean if bn1 else None),
+           _vp(bn1.invstd if bn1 else None), _vp(residual), _vp(out), n, h, w, c, pool, int(relu), int(train),
+           C.c_float(momentum), C.c_float(eps))
+    return out
+
+
+def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False):
+    """Returns (dy, dy1|None, g|None); accumulates dgamma/dbeta into bn.dgamma/bn.dbeta (fp32, pre-zeroed)."""
+    n, h, w, c = y.shape
+    dy = torch.empty_like(y)
+    dy1 = torch.empty_like(y1) if y1 is not None else None
+    g = torch.empty_like(y) if want_g else None
+    L.call("tris_bn_bwd", _vp(dout), _vp(out), _vp(y), _vp(bn.gamma), _vp(bn.beta), _vp(bn.mean), _vp(bn.invstd),
+           _vp(bn.dgamma), _vp(bn.dbeta), _vp(dy), _vp(y1), _vp(bn1.gamma if bn1 else None),
+           _vp(bn1.beta if bn1 else None), _vp(bn1.mean if bn1 else None), _vp(bn1.invstd if bn1 else None),
+           _vp(bn1.dgamma if bn1 else None), _vp(bn1.dbeta if bn1 else None), _vp(dy1), _vp(g), n, h, w, c, pool,
+           int(relu), launches=2)
+    return dy, dy1, g
+
+
+def avgpool2(x):
+    n, h, w, c = x.shape
+    out = empty((n, h // 2, w // 2, c), x)
+    L.call("tris_avgpool2_fwd", _vp(x), _vp(out), n, h, w, c)
+    return out
+
+
+def avgpool2_bwd(dout, add=None):
+    n, ho, wo, c = dout.shape
+    dx = empty((n, ho * 2, wo * 2, c), dout)
+    L.call("tris_avgpool2_bwd", _vp(dout), _vp(add), _vp(dx), n, ho * 2, wo * 2, c)
+    return dx
+
+
+# ------------------------------------------------------------------ transformer pieces
+def embed_fwd(ids, E, Ppos, want_eot=True):
+    n, l = ids.shape
+    d = E.shape[1]
+    x = torch.empty((n * l, d), device=E.device, dtype=bf16)
+    eot = torch.empty((n,), device=E.device, dtype=torch.int32) if want_eot else None
+    L.call("tris_embed_fwd", _vp(ids), _vp(E), _vp(Ppos), _vp(x), _vp(eot), n, l, d)
+    return x, eot
+
+
+def embed_bwd(ids, dx, dE, dP):
+    n, l = ids.shape
+    L.call("tris_embed_bwd", _vp(ids), _vp(dx), _vp(dE), _vp(dP), n, l, dE.shape[1])
+
+
+def layernorm_fwd(x, gamma, beta, save=True, eps=1e-5):
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((rows,), device=x.device, dtype=f32) if save else None
+    rstd = torch.empty((rows,), device=x.device, dtype=f32) if save else None
+    L.call("tris_layernorm_fwd", _vp(x), _vp(gamma), _vp(beta), _vp(y), _vp(mean), _vp(rstd), rows, d, C.c_float(eps))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None):
+    rows, d = x.shape
+    dx = torch.empty_like(x)
+    L.call("tris_layernorm_bwd", _vp(dy), _vp(x), _vp(gamma), _vp(mean), _vp(rstd), _vp(add), _vp(dx), _vp(dgamma),
+           _vp(dbeta), rows, d)
+    return dx
+
+
+def attn_fwd(qkv, n, l, heads, causal):
+    out = torch.empty((n * l, heads * 64), device=qkv.device, dtype=bf16)
+    L.call("tris_attn_fwd", _vp(qkv), _vp(out), n, l, heads, int(causal))
+    return out
+
+
+def attn_bwd(qkv, dout, n, l, heads, causal):
+    dqkv = torch.empty_like(qkv)
+    L.call("tris_attn_bwd", _vp(qkv), _vp(dout), _vp(dqkv), n, l, heads, int(causal))
+    return dqkv
+
+
+def gather_rows(x, idx):
+    out = torch.empty((idx.numel(), x.shape[1]), device=x.device, dtype=bf16)
+    L.call("tris_gather_rows", _vp(x), _vp(idx), _vp(out), idx.numel(), x.shape[1])
+    return out
+
+
+def scatter_rows(src, idx, rows_total):
+    out = torch.zeros((rows_total, src.shape[1]), device=src.device, dtype=bf16)
+    L.call("tris_scatter_rows", _vp(src), _vp(idx), _vp(out), idx.numel(), src.shape[1])
+    return out
+
+
+def colsum(x, out):
+    L.call("tris_colsum", _vp(x), _vp(out), x.shape[0], x.shape[1])
+
+
+def vit_assemble(patch, cls, pos, n):
+    t, d = pos.shape
+    tok = torch.empty((n * t, d), device=patch.device, dtype=bf16)
+    L.call("tris_vit_assemble", _vp(patch), _vp(cls), _vp(pos), _vp(tok), n, t, d)
+    return tok
+
+
+# ------------------------------------------------------------------ misc
+def stem_im2col(img):
+    n, _, h, w = img.shape
+    col = torch.empty((n * (h // 2) * (w // 2), 64), device=img.device, dtype=bf16)
+    L.call("tris_stem_im2col", _vp(img), _vp(col), n, h, w)
+    return col
+
+
+def f32_to_bf16(src, dst):
+    L.call("tris_f32_to_bf16", _vp(src), _vp(dst), C.c_long(src.numel()))
+
+
+def pack_conv(w, out, co_pad=None, ci_pad=None):
+    co, ci, kh, kw = w.shape
+    L.call("tris_pack_conv", _vp(w), _vp(out), co, ci, kh * kw, co_pad or co, ci_pad or ci)
+
+
+def unpack_conv_grad(gp, gw, ci_pad=None):
+    co, ci, kh, kw = gw.shape
+    L.call("tris_unpack_conv_grad", _vp(gp), _vp(gw), co, ci, kh * kw, ci_pad or ci)
+
+
+def l2norm_fwd(x):
+    y = torch.empty_like(x)
+    inv = torch.empty((x.shape[0],), device=x.device, dtype=f32)
+    L.call("tris_l2norm_fwd", _vp(x), _vp(y), _vp(inv), x.shape[0], x.shape[1])
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    dx = torch.empty_like(y)
+    L.call("tris_l2norm_bwd", _vp(dy), _vp(y), _vp(inv), _vp(dx), y.shape[0], y.shape[1])
+    return dx
+
+
+def instnorm_fwd(x, gamma, beta, batch, relu, mix_scale=1.0, mix_add=None, eps=1e-5):
+    rows, c = x.shape
+    p = rows // batch
+    out = torch.empty_like(x)
+    mean = torch.empty((batch, c), device=x.device, dtype=f32)
+    invstd = torch.empty((batch, c), device=x.device, dtype=f32)
+    L.call("tris_instnorm_fwd", _vp(x), _vp(gamma), _vp(beta), _vp(mix_add), _vp(out), _vp(mean), _vp(invstd), batch, p, c,
+           C.c_float(mix_scale), int(relu), C.c_float(eps))
+    return out, mean, invstd
+
+
+def instnorm_bwd(dout, x, gamma, beta, mean, invstd, dgamma, dbeta, batch, relu, mix_scale=1.0):
+    rows, c = x.shape
+    dx = torch.empty_like(x)
+    L.call("tris_instnorm_bwd", _vp(dout), _vp(x), _vp(gamma), _vp(beta), _vp(mean), _vp(invstd), _vp(dx), _vp(dgamma),
+           _vp(dbeta), batch, rows // batch, c, C.c_float(mix_scale), int(relu))
+    return dx
+
+
+def axpby(x, y, a, b):
+    """y = a*x + b*y (bf16, in place on y)."""
+    L.call("tris_axpby", _vp(x), _vp(y), C.c_float(a), C.c_float(b), C.c_long(x.numel()))
+    return y

@@ -1,0 +1,220 @@
+"""CLIP ModifiedResNet (RN50/RN101) image tower on NHWC bf16 with hand-written kernels: forward and backward.
+
+Arithmetic restated from CLIP/clip/model.py:10-55 (Bottleneck), :212-232 + :254-279 (stem / layers) of the reference;
+the attention pool (:58-104) is NOT computed here -- Stage-1 discards it (model_stage1.py:59).
+
+Every conv is a tcgen05 GEMM (gemm.py); the first stem conv goes through an im2col of the fp32 NCHW image; the two
+32-channel stem activations are carried zero-padded to 64 channels so that every k-block is a full 128-byte TMA row.
+BatchNorm batch statistics come out of the GEMM epilogues; BN-apply/ReLU/pool/residual are one streaming kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import gemm as G
+from . import ops
+from .ops import BNState
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _Block:
+    __slots__ = ("p", "cin", "planes", "stride", "down")
+
+
+class ResNetTower:
+    def __init__(self, store, module, prefix: str, layers=(3, 4, 6, 3)):
+        self.store, self.prefix, self.layers = store, prefix, layers
+        dev = store.device
+        self.blocks: List[_Block] = []
+        inpl = 64
+        for li, (planes, nb) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+            for b in range(nb):
+                blk = _Block()
+                blk.p = f"{prefix}layer{li}.{b}."
+                blk.cin, blk.planes = inpl, planes
+                blk.stride = 2 if (b == 0 and li > 1) else 1
+                blk.down = blk.stride > 1 or inpl != planes * 4
+                self.blocks.append(blk)
+                inpl = planes * 4
+        self.out_channels = inpl
+        # ---- BN states (real ones are views of the store / module buffers)
+        self.bn: Dict[str, BNState] = {}
+        bufs = dict(module.named_buffers())
+
+        def real_bn(key):
+            return BNState(store.p(key + ".weight"), store.p(key + ".bias"), bufs[key + ".running_mean"],
+                           bufs[key + ".running_var"], store.g(key + ".weight"), store.g(key + ".bias"))
+
+        for blk in self.blocks:
+            for nm in ("bn1", "bn2", "bn3") + (("downsample.1",) if blk.down else ()):
+                self.bn[blk.p + nm] = real_bn(blk.p + nm)
+        self.bn[prefix + "bn3"] = real_bn(prefix + "bn3")
+        # padded (32 -> 64 channel) stem BNs: private fp32 copies
+        self.pad_bn: Dict[str, BNState] = {}
+        for nm in ("bn1", "bn2"):
+            z = lambda: torch.zeros(64, device=dev, dtype=f32)
+            st = BNState(z(), z(), z(), torch.ones(64, device=dev, dtype=f32), z(), z())
+            self.pad_bn[prefix + nm] = st
+        self.real_small_bn = {prefix + nm: real_bn(prefix + nm) for nm in ("bn1", "bn2")}
+        # ---- packed weights
+        self.w_stem1 = torch.zeros((64, 64), device=dev, dtype=bf16)
+        self.w_stem2 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
+        self.w_stem3 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
+        self.w3x3 = {blk.p: torch.empty((blk.planes, 9 * blk.planes), device=dev, dtype=bf16) for blk in self.blocks}
+        n_stats = 2 * (64 * 3 + sum(b.planes * 2 + b.planes * 4 * (2 if b.down else 1) for b in self.blocks))
+        self.stats_buf = torch.zeros(n_stats, device=dev, dtype=f32)
+        self.bn_keys = [k for k, _ in module.named_buffers() if k.startswith(prefix) and k.endswith("num_batches_tracked")
+                        and "attnpool" not in k]
+        self.nbt = [bufs[k] for k in self.bn_keys]
+
+    # ------------------------------------------------------------------ derived weights
+    def refresh(self):
+        """Re-derive packed / padded bf16 operands from the fp32 masters (after an optimizer step or a load)."""
+        st, p = self.store, self.prefix
+        ops.pack_conv(st.p(p + "conv1.weight"), self._tmp27())          # [32, (r,s,c)] matches stem_im2col's k order
+        self.w_stem1[:32, :27].copy_(self._tmp27())
+        ops.pack_conv(st.p(p + "conv2.weight"), self.w_stem2, co_pad=64, ci_pad=64)
+        ops.pack_conv(st.p(p + "conv3.weight"), self.w_stem3, co_pad=64, ci_pad=64)
+        for blk in self.blocks:
+            ops.pack_conv(st.p(blk.p + "conv2.weight"), self.w3x3[blk.p])
+        for k, pad in self.pad_bn.items():
+            real = self.real_small_bn[k]
+            pad.gamma[:32].copy_(real.gamma); pad.beta[:32].copy_(real.beta)
+            pad.rm[:32].copy_(real.rm); pad.rv[:32].copy_(real.rv)
+
+    def _tmp27(self):
+        if not hasattr(self, "_t27"):
+            self._t27 = torch.empty((32, 27), device=self.store.device, dtype=bf16)
+        return self._t27
+
+    def _w1x1(self, key):
+        w = self.store.s(key)
+        return w.view(w.shape[0], w.shape[1])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img: torch.Tensor, train: bool):
+        """img fp32 NCHW [B,3,H,W] -> (c4 bf16 NHWC [B,H/32,W/32,2048], tape)."""
+        p = self.prefix
+        B, _, H, W = img.shape
+        tape = {} if train else None
+        so = [0]
+        if train:
+            self.stats_buf.zero_()
+
+        def stats(c):
+            if not train:
+                return None
+            s = self.stats_buf[so[0]: so[0] + 2 * c]
+            so[0] += 2 * c
+            return s
+
+        col = ops.stem_im2col(img.contiguous())
+        s = stats(64)
+        y1 = G.linear_fwd(col, self.w_stem1, stats=s).view(B, H // 2, W // 2, 64)
+        a1 = ops.bn_apply(y1, s, self.pad_bn[p + "bn1"], train)
+        s2 = stats(64)
+        y2 = G.conv3x3_fwd(a1, self.w_stem2, stats=s2)
+        a2 = ops.bn_apply(y2, s2, self.pad_bn[p + "bn2"], train)
+        s3 = stats(64)
+        y3 = G.conv3x3_fwd(a2, self.w_stem3, stats=s3)
+        x = ops.bn_apply(y3, s3, self.bn[p + "bn3"], train, pool=2)
+        if train:
+            tape["stem"] = (col, y1, a1, y2, a2, y3)
+            for nm in ("bn1", "bn2"):   # running stats of the padded copies back into the real buffers
+                pad, real = self.pad_bn[p + nm], self.real_small_bn[p + nm]
+                real.rm.copy_(pad.rm[:32]); real.rv.copy_(pad.rv[:32])
+        feats = []
+        for blk in self.blocks:
+            x, rec = self._block_fwd(blk, x, train, stats)
+            if train:
+                tape[blk.p] = rec
+        if train:
+            torch._foreach_add_(self.nbt, 1)
+        return x, tape
+
+    def _block_fwd(self, blk: _Block, x, train, stats):
+        B, H, W, Cin = x.shape
+        pl, q = blk.planes, blk.p
+        s1 = stats(pl)
+        y1 = G.linear_fwd(x.view(-1, Cin), self._w1x1(q + "conv1.weight"), stats=s1).view(B, H, W, pl)
+        a1 = ops.bn_apply(y1, s1, self.bn[q + "bn1"], train)
+        s2 = stats(pl)
+        y2 = G.conv3x3_fwd(a1, self.w3x3[q], stats=s2)
+        a2 = ops.bn_apply(y2, s2, self.bn[q + "bn2"], train, pool=blk.stride)
+        Ho, Wo = H // blk.stride, W // blk.stride
+        s3 = stats(4 * pl)
+        y3 = G.linear_fwd(a2.view(-1, pl), self._w1x1(q + "conv3.weight"), stats=s3).view(B, Ho, Wo, 4 * pl)
+        xp = yd = None
+        if blk.down:
+            xp = ops.avgpool2(x) if blk.stride > 1 else x
+            sd = stats(4 * pl)
+            yd = G.linear_fwd(xp.view(-1, Cin), self._w1x1(q + "downsample.0.weight"), stats=sd).view(B, Ho, Wo, 4 * pl)
+            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, y1=yd, stats1=sd, bn1=self.bn[q + "downsample.1"])
+        else:
+            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, residual=x)
+        return out, ((x, y1, a1, y2, a2, y3, xp, yd, out) if train else None)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, tape, dout: torch.Tensor):
+        """dout: gradient w.r.t. c4 (bf16 NHWC).  Writes all parameter gradients into the store."""
+        st, p = self.store, self.prefix
+        for blk in reversed(self.blocks):
+            dout = self._block_bwd(blk, tape[blk.p], dout)
+        col, y1, a1, y2, a2, y3 = tape["stem"]
+        dy3, _, _ = ops.bn_bwd(dout, None, y3, self.bn[p + "bn3"], pool=2)
+        self._wgrad3x3(dy3, a2, p + "conv3.weight", ci_pad=64)
+        da2 = G.conv3x3_dgrad(dy3, self.w_stem3, 64)
+        pb2 = self.pad_bn[p + "bn2"]
+        pb2.dgamma.zero_(); pb2.dbeta.zero_()
+        dy2, _, _ = ops.bn_bwd(da2, None, y2, pb2)
+        self._wgrad3x3(dy2, a1, p + "conv2.weight", ci_pad=64)
+        da1 = G.conv3x3_dgrad(dy2, self.w_stem2, 64)
+        pb1 = self.pad_bn[p + "bn1"]
+        pb1.dgamma.zero_(); pb1.dbeta.zero_()
+        dy1, _, _ = ops.bn_bwd(da1, None, y1, pb1)
+        gw = G.linear_wgrad(dy1.view(-1, 64), col)                       # [64, 64] fp32
+        g1 = st.g(p + "conv1.weight")                                    # [32,3,3,3]
+        g1.add_(gw[:32, :27].reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+        for nm, pad in (("bn1", pb1), ("bn2", pb2)):
+            st.g(p + nm + ".weight").add_(pad.dgamma[:32])
+            st.g(p + nm + ".bias").add_(pad.dbeta[:32])
+
+    def _wgrad3x3(self, dy, x, key, ci_pad=None):
+        gw = self.store.g(key)
+        gp = G.conv3x3_wgrad(dy, x)
+        ops.unpack_conv_grad(gp, gw, ci_pad=ci_pad)
+
+    def _wgrad1x1(self, dy2d, x2d, key):
+        gw = self.store.g(key)
+        G.linear_wgrad(dy2d, x2d, out=gw.view(gw.shape[0], gw.shape[1]), accumulate=True)
+
+    def _block_bwd(self, blk: _Block, rec, dout):
+        x, y1, a1, y2, a2, y3, xp, yd, out = rec
+        q, pl = blk.p, blk.planes
+        Cin = x.shape[3]
+        if blk.down:
+            dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], y1=yd, bn1=self.bn[q + "downsample.1"])
+        else:
+            dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], want_g=True)
+        self._wgrad1x1(dy3.view(-1, 4 * pl), a2.view(-1, pl), q + "conv3.weight")
+        da2 = G.linear_dgrad(dy3.view(-1, 4 * pl), self._w1x1(q + "conv3.weight")).view(a2.shape)
+        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.bn[q + "bn2"], pool=blk.stride)
+        self._wgrad3x3(dy2, a1, q + "conv2.weight")
+        da1 = G.conv3x3_dgrad(dy2, self.w3x3[q], pl)
+        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.bn[q + "bn1"])
+        self._wgrad1x1(dy1.view(-1, pl), x.view(-1, Cin), q + "conv1.weight")
+        w1 = self._w1x1(q + "conv1.weight")
+        if blk.down:
+            self._wgrad1x1(dyd.view(-1, 4 * pl), xp.view(-1, Cin), q + "downsample.0.weight")
+            dxp = G.linear_dgrad(dyd.view(-1, 4 * pl), self._w1x1(q + "downsample.0.weight"))
+            if blk.stride > 1:
+                dx = G.linear_dgrad(dy1.view(-1, pl), w1).view(x.shape)
+                dx = ops.avgpool2_bwd(dxp.view(xp.shape), add=dx)
+            else:
+                dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=dxp).view(x.shape)
+        else:
+            dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin)).view(x.shape)
+        return dx

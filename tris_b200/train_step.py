@@ -1,0 +1,124 @@
+"""One Stage-1 training step: forward, the three CLIP-guided losses, backward, gradient all-reduce, fused AdamW.
+
+Restates the loop body of train_stage1.py:320-372 (fg / cls / negative losses, weights w1,w4,w5; AdamW with two
+learning-rate groups and the per-step poly-0.9 schedule).  Differences, all deliberate:
+  * the frozen auxiliary ViT-B/32 image tower runs ONCE per step (the reference encodes the same fg twice) and its
+    backward is data-gradient only; the auxiliary text tower runs once on [B*(1+negs), L] without a graph;
+  * data parallelism = one NCCL all-reduce over the flat gradient buffer, BatchNorm statistics stay per rank.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _lib as L
+
+f32 = torch.float32
+
+
+def mask_and_resize(sig_out, img, size=224):
+    """train_stage1.py:327-339 (fg only; the bg branch is dead code in the reference)."""
+    if img.shape[2] != size:
+        cam = F.interpolate(sig_out, (size, size), mode="bilinear", align_corners=True)
+        im = F.interpolate(img, (size, size), mode="bilinear", align_corners=True)
+    else:
+        cam, im = sig_out, img
+    return cam * im
+
+
+def stage1_losses(model, aux, img, word_ids, neg_word_ids, w1=1.0, w4=5.0, w5=2.0):
+    """-> dict(loss, l1, l4, l5) as device scalars (no host sync)."""
+    B = img.shape[0]
+    cls, _, _, sig_out, _ = model(img, word_ids)
+    fg = mask_and_resize(sig_out, img)
+    f = aux.encode_image(fg)
+    f = f / f.norm(dim=-1, keepdim=True)
+    ids = word_ids if neg_word_ids is None else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
+    g = aux._engine().encode_text_hidden(ids).float()
+    g = g / g.norm(dim=-1, keepdim=True)
+    cos = (f * g[:B]).sum(-1)
+    l1 = -torch.log(cos.clamp(0.0001, 0.9999)).mean()
+    if neg_word_ids is not None:
+        k = neg_word_ids.shape[1]
+        nscore = torch.einsum("bc,bkc->bk", f, g[B:].reshape(B, k, -1))
+        l5 = (-torch.log(1 - nscore)).mean()
+    else:
+        l5 = torch.zeros((), device=img.device)
+    l4 = F.multilabel_soft_margin_loss(cls, torch.eye(B, device=img.device, dtype=cls.dtype))
+    return {"loss": l1 * w1 + l4 * w4 + l5 * w5, "l1": l1, "l4": l4, "l5": l5}
+
+
+class Stage1Trainer:
+    def __init__(self, model, aux, max_iter: int, lr=5e-5, lr_multi=0.1, weight_decay=0.01, w=(1.0, 5.0, 2.0),
+                 process_group=None):
+        self.model, self.aux, self.w = model, aux, w
+        self.eng = model.engine()
+        st = self.eng.store
+        self.m = torch.zeros(st.n_train, device=st.device, dtype=f32)
+        self.v = torch.zeros(st.n_train, device=st.device, dtype=f32)
+        self.step_count = torch.zeros(1, device=st.device, dtype=torch.int32)
+        self.max_iter, self.lr, self.lr_multi, self.wd = float(max_iter), lr, lr_multi, weight_decay
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.pg = process_group
+        self.graph = None
+        self.static = None
+        st.publish_grads()            # param.grad = views of the flat buffer; the trainer zeroes the buffer itself
+        for k in self.eng.extra_grad_keys:
+            st.params[k].grad = st.g(k)
+
+    def optimizer_step(self):
+        st = self.eng.store
+        if self.world > 1:
+            dist.all_reduce(st.grad[: st.n_train], group=self.pg)
+        L.call("tris_adamw_step", C.c_void_p(st.flat.data_ptr()), C.c_void_p(st.grad.data_ptr()), C.c_void_p(self.m.data_ptr()),
+               C.c_void_p(self.v.data_ptr()), C.c_void_p(st.shadow.data_ptr()), C.c_long(st.n_train),
+               C.c_long(st.group_bounds[1]), C.c_void_p(self.step_count.data_ptr()), C.c_float(self.max_iter),
+               C.c_float(self.lr * self.lr_multi), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8),
+               C.c_float(self.wd), C.c_float(1.0 / self.world), C.c_float(0.9), launches=2)
+        self.eng._seen_versions = None   # masters changed behind torch's back: re-derive packed operands next forward
+
+    def _fwd_bwd(self, img, word_ids, neg_word_ids):
+        self.model.train()
+        self.eng.store.zero_grad()
+        losses = stage1_losses(self.model, self.aux, img, word_ids, neg_word_ids, *self.w)
+        losses["loss"].backward()
+        return losses
+
+    def _step_eager(self, img, word_ids, neg_word_ids):
+        losses = self._fwd_bwd(img, word_ids, neg_word_ids)
+        self.optimizer_step()
+        return losses
+
+    def step(self, img, word_ids, neg_word_ids):
+        """One optimisation step on device-resident inputs; returns device scalars."""
+        if self.graph is None:
+            return self._step_eager(img, word_ids, neg_word_ids)
+        s_img, s_ids, s_neg, s_out = self.static
+        s_img.copy_(img, non_blocking=True)
+        s_ids.copy_(word_ids, non_blocking=True)
+        if s_neg is not None:
+            s_neg.copy_(neg_word_ids, non_blocking=True)
+        self.graph.replay()
+        if self.world > 1:            # the NCCL all-reduce + AdamW stay outside the graph in multi-rank runs
+            self.optimizer_step()
+        return s_out
+
+    def capture(self, img, word_ids, neg_word_ids, warmup=3):
+        """Capture the whole step (fwd + bwd + all-reduce + AdamW) into one CUDA graph (static shapes)."""
+        s_img, s_ids = img.clone(), word_ids.clone()
+        s_neg = neg_word_ids.clone() if neg_word_ids is not None else None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_eager(s_img, s_ids, s_neg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._step_eager(s_img, s_ids, s_neg) if self.world == 1 else self._fwd_bwd(s_img, s_ids, s_neg)
+        self.graph, self.static = g, (s_img, s_ids, s_neg, out)
+        return self
