@@ -427,6 +427,12 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     const long total = static_cast<long>(n) * h * w * (c / 8);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static bool attr = false;
+    if (!attr) {
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+    }
     // cap the reduction grid: each block ends with 2-4 * C atomics
     int rgrid = grid_for(total);
     if (rgrid > 2 * tris::sm_count()) rgrid = 2 * tris::sm_count();

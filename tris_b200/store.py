@@ -49,7 +49,7 @@ class ParamStore:
         self.n_train = self.group_bounds[2]
         self.device = torch.device(device)
         self.flat = torch.zeros(self.total, device=self.device, dtype=torch.float32)
-        self.grad = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros(self.total if self.n_train > 0 else 8, device=self.device, dtype=torch.float32)
         self.shadow = torch.zeros(self.total, device=self.device, dtype=torch.bfloat16)
         self.params: Dict[str, nn.Parameter] = {}
         with torch.no_grad():
@@ -60,6 +60,7 @@ class ParamStore:
                 p.grad = None
                 self.params[k] = p
         self.trainable = [k for k, _ in ordered if self.offsets[k] < self.n_train]
+        self._probe = ordered[0][0]
         self.shadow_valid = False
         self._versions = None
 
@@ -73,6 +74,8 @@ class ParamStore:
         return self._view(self.flat, k)
 
     def g(self, k):
+        if self.n_train == 0:
+            return None
         return self._view(self.grad, k)
 
     def s(self, k):
@@ -91,7 +94,7 @@ class ParamStore:
 
     # ---- maintenance
     def still_bound(self) -> bool:
-        k = self.trainable[0]
+        k = self._probe
         return self.params[k].data_ptr() == self.p(k).data_ptr()
 
     def refresh_shadow(self):
