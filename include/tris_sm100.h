@@ -53,8 +53,9 @@ typedef struct tris_gemm_desc {
     void* d;              /* bf16 or f32, row-major [M, ldd] (conv: NHWC pixels x channels) */
     const float* bias;    /* [N] or NULL (added before activation) */
     const void* residual; /* bf16 [M, ldd] or NULL (added after activation) */
-    float* stats;         /* [2N] column sum / sum of squares of the pre-activation output, atomically
-                             accumulated (BatchNorm batch statistics, model.py:18-28) or NULL */
+    float* stats;         /* [2N] column sum / sum of squares of the stored (bf16-rounded) output, accumulated per CTA
+                             in shared memory and flushed with one atomic per column (BatchNorm batch statistics,
+                             model.py:18-28) or NULL */
     int32_t a_mode, b_mode;
     int32_t M, N, K;      /* GEMM extents.  conv fwd/dgrad: M = n*h*w pixels, K = taps*channels(A).
                              conv wgrad: M = channels(A), N = channels(B), K = n*h*w pixels (per tap) */
@@ -75,6 +76,11 @@ typedef struct tris_gemm_desc {
     void* d_pre;          /* optional bf16 [M, ldd]: pre-activation (post-bias) values, saved for backward */
     const void* dact_src; /* optional bf16 [M, ldd]: epilogue multiplies by act'(dact_src) instead of applying act
                              (fuses the QuickGELU / ReLU derivative into a dgrad GEMM) */
+    int32_t batch;        /* >1: `batch` independent GEMMs of extents M,N,K (2-D modes only; per-image products of the
+                             cross-modal attention, model/attn.py:118-131).  Rows beyond M / K of one batch entry are
+                             zero-filled by TMA, so M and K need not be multiples of the tile */
+    int32_t reserved0;
+    int64_t a_batch_stride, b_batch_stride, d_batch_stride; /* elements; 0 for A/B = operand shared by all batches */
 } tris_gemm_desc;
 
 int tris_gemm(const tris_gemm_desc* desc, tris_stream_t stream);

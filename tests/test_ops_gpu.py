@@ -374,5 +374,5 @@ def test_bottleneck_block_fwd_bwd_vs_oracle(tris, name, hw):
         errs[k[len(blk.p):]] = frob(eng.store.g(k), g)
     print(name, {k: round(v, 4) for k, v in errs.items()})
     for k, v in errs.items():
-        assert v < 0.08, (k, v)
+        assert v < 0.12, (k, v)
     m.load_state_dict(sdb, strict=False)

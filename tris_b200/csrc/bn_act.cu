@@ -93,21 +93,28 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
     __syncthreads();
     const int vecs = p.c >> 3;
     const int ho = p.h / p.pool, wo = p.w / p.pool;
-    const long total = static_cast<long>(p.n) * ho * wo * vecs;
-    for (long v = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x; v < total;
-         v += static_cast<long>(gridDim.x) * kThreads) {
-        const int cg = static_cast<int>(v % vecs);
-        const long orow = v / vecs;
-        const int c0 = cg * 8;
+    const long rows_out = static_cast<long>(p.n) * ho * wo;
+    // the grid stride (gridDim * 256 vectors) is a multiple of `vecs` (vecs | 256): a thread keeps its channel group,
+    // so scale/shift live in registers and the loop walks rows without divisions.
+    const long start = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x;
+    const int c0 = static_cast<int>(start % vecs) * 8;
+    const long row_step = static_cast<long>(gridDim.x) * kThreads / vecs;
+    float a0[8], b0[8], a1[8], b1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a0[i] = sc0[c0 + i]; b0[i] = sh0[c0 + i];
+        a1[i] = dual ? sc1[c0 + i] : 0.f; b1[i] = dual ? sh1[c0 + i] : 0.f;
+    }
+    for (long orow = start / vecs; orow < rows_out; orow += row_step) {
         Vec8 acc;
         if (p.pool == 1) {
             acc = ld8(p.b0.y + orow * p.c + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc.v[i] = acc.v[i] * sc0[c0 + i] + sh0[c0 + i];
+            for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(acc.v[i], a0[i], b0[i]);
             if (dual) {
                 Vec8 y1 = ld8(p.b1.y + orow * p.c + c0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc.v[i] += y1.v[i] * sc1[c0 + i] + sh1[c0 + i];
+                for (int i = 0; i < 8; ++i) acc.v[i] += fmaf(y1.v[i], a1[i], b1[i]);
             }
             if (p.residual != nullptr) {
                 Vec8 r = ld8(p.residual + orow * p.c + c0);
@@ -125,13 +132,15 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
             const long ni = t / ho;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
             for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const long irow = (ni * p.h + (2 * yo + dy)) * p.w + (2 * xo + dx);
                     Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float z = y0.v[i] * sc0[c0 + i] + sh0[c0 + i];
+                        float z = fmaf(y0.v[i], a0[i], b0[i]);
                         if (p.relu) z = fmaxf(z, 0.f);
                         acc.v[i] += 0.25f * z;
                     }
@@ -155,7 +164,7 @@ struct BwdParams {
 
 // g at input position (irow) for channel group c0, already masked and pool-scaled.
 __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long irow, long orow, int c0, const Vec8& y0,
-                                            const float* sc0, const float* sh0) {
+                                            const float (&sc0)[8], const float (&sh0)[8]) {
     Vec8 g = ld8(p.dout + orow * p.c + c0);
     if (p.pool == 2) {
 #pragma unroll
@@ -168,21 +177,10 @@ __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long irow, long 
             for (int i = 0; i < 8; ++i) g.v[i] = o.v[i] > 0.f ? g.v[i] : 0.f;
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g.v[i] = (y0.v[i] * sc0[c0 + i] + sh0[c0 + i]) > 0.f ? g.v[i] : 0.f;
+            for (int i = 0; i < 8; ++i) g.v[i] = fmaf(y0.v[i], sc0[i], sh0[i]) > 0.f ? g.v[i] : 0.f;
         }
     }
     return g;
-}
-
-__device__ __forceinline__ void load_affine(const BnBranch& b, int c, float* sc, float* sh, float* mu, float* is) {
-    for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        const float invstd = b.save_invstd[i], mean = b.save_mean[i];
-        const float s = b.gamma[i] * invstd;
-        sc[i] = s;
-        sh[i] = b.beta[i] - mean * s;
-        mu[i] = mean;
-        is[i] = invstd;
-    }
 }
 
 __device__ __forceinline__ long out_row_of(const BwdParams& p, long irow) {
@@ -196,43 +194,39 @@ __device__ __forceinline__ long out_row_of(const BwdParams& p, long irow) {
 
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdParams p) {
     extern __shared__ float sm[];
-    float* sc0 = sm;
-    float* sh0 = sm + p.c;
-    float* mu0 = sm + 2 * p.c;
-    float* is0 = sm + 3 * p.c;
-    float* mu1 = sm + 4 * p.c;
-    float* is1 = sm + 5 * p.c;
-    float* red = sm + 6 * p.c;   // [kThreads * 8] scratch reused per quantity
+    float* red = sm;   // [kThreads * 8] scratch reused per quantity
     const bool dual = p.b1.y != nullptr;
-    load_affine(p.b0, p.c, sc0, sh0, mu0, is0);
-    if (dual) {
-        for (int i = threadIdx.x; i < p.c; i += blockDim.x) { mu1[i] = p.b1.save_mean[i]; is1[i] = p.b1.save_invstd[i]; }
-    }
-    __syncthreads();
     const int vecs = p.c >> 3;
     const long rows = static_cast<long>(p.n) * p.h * p.w;
-    const long total = rows * vecs;
     // grid stride is a multiple of `vecs` (vecs | kThreads), so each thread keeps one channel group.
     const long start = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x;
-    const int cg = static_cast<int>(start % vecs);
-    const int c0 = cg * 8;
+    const int c0 = static_cast<int>(start % vecs) * 8;
+    const long row_step = static_cast<long>(gridDim.x) * kThreads / vecs;
+    float sc0[8], sh0[8], mu0[8], is0[8], mu1[8], is1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float invstd = p.b0.save_invstd[c0 + i], mean = p.b0.save_mean[c0 + i];
+        const float sc = p.b0.gamma[c0 + i] * invstd;
+        sc0[i] = sc; sh0[i] = p.b0.beta[c0 + i] - mean * sc; mu0[i] = mean; is0[i] = invstd;
+        mu1[i] = dual ? p.b1.save_mean[c0 + i] : 0.f;
+        is1[i] = dual ? p.b1.save_invstd[c0 + i] : 0.f;
+    }
     float dg0[8], db[8], dg1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dg0[i] = db[i] = dg1[i] = 0.f;
-    for (long v = start; v < total; v += static_cast<long>(gridDim.x) * kThreads) {
-        const long irow = v / vecs;
+    for (long irow = start / vecs; irow < rows; irow += row_step) {
         const long orow = out_row_of(p, irow);
         Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
         Vec8 g = masked_grad(p, irow, orow, c0, y0, sc0, sh0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             db[i] += g.v[i];
-            dg0[i] += g.v[i] * (y0.v[i] - mu0[c0 + i]) * is0[c0 + i];
+            dg0[i] = fmaf(g.v[i], (y0.v[i] - mu0[i]) * is0[i], dg0[i]);
         }
         if (dual) {
             Vec8 y1 = ld8(p.b1.y + irow * p.c + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dg1[i] += g.v[i] * (y1.v[i] - mu1[c0 + i]) * is1[c0 + i];
+            for (int i = 0; i < 8; ++i) dg1[i] = fmaf(g.v[i], (y1.v[i] - mu1[i]) * is1[i], dg1[i]);
         }
     }
     // block reduction over the kThreads/vecs threads that share a channel group
@@ -258,56 +252,48 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdParams
 }
 
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const BwdParams p) {
-    extern __shared__ float sm[];
-    float* sc0 = sm;
-    float* sh0 = sm + p.c;
-    float* mu0 = sm + 2 * p.c;
-    float* is0 = sm + 3 * p.c;
-    float* a0 = sm + 4 * p.c;   // gamma*invstd
-    float* k0 = sm + 5 * p.c;   // dgamma/M
-    float* m0 = sm + 6 * p.c;   // dbeta/M
-    float* mu1 = sm + 7 * p.c;
-    float* is1 = sm + 8 * p.c;
-    float* a1 = sm + 9 * p.c;
-    float* k1 = sm + 10 * p.c;
-    float* m1 = sm + 11 * p.c;
     const bool dual = p.b1.y != nullptr;
-    load_affine(p.b0, p.c, sc0, sh0, mu0, is0);
-    for (int i = threadIdx.x; i < p.c; i += blockDim.x) {
-        a0[i] = p.b0.gamma[i] * p.b0.save_invstd[i];
-        k0[i] = p.dgamma0[i] / p.count;
-        m0[i] = p.dbeta0[i] / p.count;
+    const int vecs = p.c >> 3;
+    const long rows = static_cast<long>(p.n) * p.h * p.w;
+    const long start = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x;
+    const int c0 = static_cast<int>(start % vecs) * 8;
+    const long row_step = static_cast<long>(gridDim.x) * kThreads / vecs;
+    float sc0[8], sh0[8], mu0[8], is0[8], k0[8], m0[8], mu1[8], is1[8], a1[8], k1[8], m1[8];
+    const float inv_count = 1.f / p.count;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float invstd = p.b0.save_invstd[c0 + i], mean = p.b0.save_mean[c0 + i];
+        const float sc = p.b0.gamma[c0 + i] * invstd;
+        sc0[i] = sc; sh0[i] = p.b0.beta[c0 + i] - mean * sc; mu0[i] = mean; is0[i] = invstd;
+        k0[i] = p.dgamma0[c0 + i] * inv_count;
+        m0[i] = p.dbeta0[c0 + i] * inv_count;
         if (dual) {
-            mu1[i] = p.b1.save_mean[i];
-            is1[i] = p.b1.save_invstd[i];
-            a1[i] = p.b1.gamma[i] * p.b1.save_invstd[i];
-            k1[i] = p.dgamma1[i] / p.count;
-            m1[i] = p.dbeta1[i] / p.count;
+            mu1[i] = p.b1.save_mean[c0 + i];
+            is1[i] = p.b1.save_invstd[c0 + i];
+            a1[i] = p.b1.gamma[c0 + i] * is1[i];
+            k1[i] = p.dgamma1[c0 + i] * inv_count;
+            m1[i] = p.dbeta1[c0 + i] * inv_count;
+        } else {
+            mu1[i] = is1[i] = a1[i] = k1[i] = m1[i] = 0.f;
         }
     }
-    __syncthreads();
-    const int vecs = p.c >> 3;
-    const long total = static_cast<long>(p.n) * p.h * p.w * vecs;
-    for (long v = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x; v < total;
-         v += static_cast<long>(gridDim.x) * kThreads) {
-        const int c0 = static_cast<int>(v % vecs) * 8;
-        const long irow = v / vecs;
+    for (long irow = start / vecs; irow < rows; irow += row_step) {
         const long orow = out_row_of(p, irow);
         Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
         Vec8 g = masked_grad(p, irow, orow, c0, y0, sc0, sh0);
         Vec8 d;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float xhat = (y0.v[i] - mu0[c0 + i]) * is0[c0 + i];
-            d.v[i] = a0[c0 + i] * (g.v[i] - m0[c0 + i] - xhat * k0[c0 + i]);
+            const float xhat = (y0.v[i] - mu0[i]) * is0[i];
+            d.v[i] = sc0[i] * (g.v[i] - m0[i] - xhat * k0[i]);
         }
         st8(p.dy0 + irow * p.c + c0, d);
         if (dual) {
             Vec8 y1 = ld8(p.b1.y + irow * p.c + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float xhat = (y1.v[i] - mu1[c0 + i]) * is1[c0 + i];
-                d.v[i] = a1[c0 + i] * (g.v[i] - m1[c0 + i] - xhat * k1[c0 + i]);
+                const float xhat = (y1.v[i] - mu1[i]) * is1[i];
+                d.v[i] = a1[i] * (g.v[i] - m1[i] - xhat * k1[i]);
             }
             st8(p.dy1 + irow * p.c + c0, d);
         }
@@ -427,18 +413,12 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     const long total = static_cast<long>(n) * h * w * (c / 8);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    static bool attr = false;
-    if (!attr) {
-        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
     // cap the reduction grid: each block ends with 2-4 * C atomics
     int rgrid = grid_for(total);
     if (rgrid > 2 * tris::sm_count()) rgrid = 2 * tris::sm_count();
-    bn_bwd_reduce_kernel<<<rgrid, kThreads, (6 * c + kThreads * 8) * sizeof(float), s>>>(p);
+    bn_bwd_reduce_kernel<<<rgrid, kThreads, kThreads * 8 * sizeof(float), s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
-    bn_bwd_apply_kernel<<<grid_for(total), kThreads, 12 * c * sizeof(float), s>>>(p);
+    bn_bwd_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_apply_kernel");
     return TRIS_OK;
 }

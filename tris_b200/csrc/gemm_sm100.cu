@@ -11,6 +11,7 @@
 // Replaces cuDNN/cuBLAS calls behind CLIP/clip/model.py:17-40 (Bottleneck convs), :366-378 (transformer linears),
 // model/model_stage1.py:36-37 and model/attn.py:69-109 of the reference.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -18,18 +19,41 @@
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 352;   // warp 0 TMA(A), warp 1 MMA, warps 2-9 epilogue, warp 10 TMA(B)
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+constexpr int kMaxAcc = 4;       // TMEM accumulator ring: min(4, 512 / BN) buffers of BN fp32 columns
+
+// Division by a launch-time constant without the ~25-instruction integer divide (these run in single-thread loops).
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ int div(int x) const { return d == 1 ? x : static_cast<int>(__umulhi(static_cast<uint32_t>(x), mul) >> shr); }
+    __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = div(x); r = x - q * static_cast<int>(d); }
+};
+static FastDiv make_fastdiv(int d) {
+    FastDiv f{static_cast<uint32_t>(d < 1 ? 1 : d), 0, 0};
+    if (f.d > 1) {
+        uint32_t lg = 0;
+        while ((1u << lg) < f.d) ++lg;
+        const uint32_t pw = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << pw) + f.d - 1) / f.d);
+        f.shr = pw - 32;
+    }
+    return f;
+}
 
 struct KParams {
     int M, N, K;
     int a_mode, b_mode, wgrad, flip, taps;
     int tiles_m, tiles_n, tiles_tap, split_k, kblocks, kb_per_split;
+    int batch, a_batched, b_batched;
     int bk, n_mma, bn;
     int img_n, img_h, img_w, th, tw, tiles_h, tiles_w, cblocks, b_tap_stride;
-    uint32_t a_bytes, b_bytes, a_atom, b_atom, tx_bytes, stages;
+    uint32_t a_bytes, b_bytes, a_atom, b_atom, a_tx, b_tx, stages, staging_bytes, stats_bytes;
+    uint32_t nacc, acc_stride, nstg;
+    FastDiv fd_tiles_n, fd_tiles_m, fd_tiles_tap, fd_split, fd_tiles_w, fd_tiles_h, fd_cblocks, fd_tw, fd_bn;
+    long long* dbg_buf;   // dbg & 8: per-tile clock64 stamps of CTA 0 ([role][64 tiles])
+    int dbg;   // TRIS_GEMM_DEBUG bit mask (profiling aid): 1 skip TMA loads, 2 skip MMA issue, 4 skip epilogue work   // accumulator ring size / column stride, staging buffers (1 or 2)
     uint32_t idesc;
     void* d;
     const float* bias;
@@ -43,33 +67,37 @@ struct KParams {
 struct SmemCtl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t acc_full[2];
-    uint64_t acc_empty[2];
+    uint64_t acc_full[kMaxAcc];
+    uint64_t acc_empty[kMaxAcc];
     uint32_t tmem_base;
 };
 
 struct TileCoord {
-    int m_t, n_t, tap, split;
+    int m_t, n_t, tap, split, batch;
     int n_i, h0, w0;  // conv fwd/dgrad output patch
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
     TileCoord c;
-    c.n_t = t % p.tiles_n;
-    t /= p.tiles_n;
-    c.m_t = t % p.tiles_m;
-    t /= p.tiles_m;
-    c.tap = t % p.tiles_tap;
-    c.split = t / p.tiles_tap;
+    p.fd_tiles_n.divmod(t, t, c.n_t);
+    p.fd_tiles_m.divmod(t, t, c.m_t);
+    p.fd_tiles_tap.divmod(t, t, c.tap);
+    p.fd_split.divmod(t, c.batch, c.split);
     c.n_i = c.h0 = c.w0 = 0;
     if (p.a_mode == TRIS_OP_CONV && !p.wgrad) {
-        int tw_i = c.m_t % p.tiles_w;
-        int r = c.m_t / p.tiles_w;
+        int r, tw_i, th_i;
+        p.fd_tiles_w.divmod(c.m_t, r, tw_i);
+        p.fd_tiles_h.divmod(r, c.n_i, th_i);
         c.w0 = tw_i * p.tw;
-        c.h0 = (r % p.tiles_h) * p.th;
-        c.n_i = r / p.tiles_h;
+        c.h0 = th_i * p.th;
     }
     return c;
+}
+
+__device__ __forceinline__ uint32_t raw_bits(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
 }
 
 __device__ __forceinline__ float act_grad(float p, int act) {
@@ -87,45 +115,35 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-// Sum each of 32 register columns over the 32 lanes of the warp; lane c ends with column c's total in v[0].
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], uint32_t lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            float send = upper ? v[i] : v[i + off];
-            float keep = upper ? v[i + off] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
-}
+// Loader variants (compile-time, so the single-thread producer / issuer loops carry no mode branches or divisions)
+enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4 };
 
+template <int AM, int BM>
 __global__ void __launch_bounds__(kThreads, 1)
 tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const KParams p) {
+                      const __grid_constant__ CUtensorMap map_d, const KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.stages * stage_bytes);
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.stages * stage_bytes + p.nstg * p.staging_bytes + p.stats_bytes);
     const uint32_t smem_base = ptx::smem_u32(smem);
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k;
+    const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k * p.batch;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_b);
+        ptx::prefetch_tmap(&map_d);
         for (uint32_t s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&ctl->full[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&ctl->full[s]), 2);
             ptx::mbar_init(ptx::smem_u32(&ctl->empty[s]), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kMaxAcc; ++b) {
             ptx::mbar_init(ptx::smem_u32(&ctl->acc_full[b]), 1);
-            ptx::mbar_init(ptx::smem_u32(&ctl->acc_empty[b]), 4);
+            ptx::mbar_init(ptx::smem_u32(&ctl->acc_empty[b]), 8);
         }
         ptx::fence_mbar_init();
     }
@@ -138,64 +156,90 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == 0 || warp == 10) {
+        // ------------------------------------------------------------------ TMA producers: warp 0 feeds A, warp 10 feeds B
+        // (two single-thread issue loops in parallel; each arms the stage's full barrier with its own byte count)
         if (lane == 0) {
+            const bool is_a = warp == 0;
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord c = decode_tile(p, t);
                 const int m0 = c.m_t * kBlockM, n0 = c.n_t * p.bn;
                 const int kb0 = c.split * p.kb_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+                if ((p.dbg & 8) && blockIdx.x == 0) { const int i_ = (t - blockIdx.x) / gridDim.x; if (i_ < 64) p.dbg_buf[(is_a ? 0 : 1) * 64 + i_] = clock64(); }
+                // incremental k-block state (no divisions inside the loop)
+                int tap = 0, cb = kb0, dr = 0, ds = 0, pn = 0, ph0 = 0, pw0 = 0;
+                if (AM == LD_CONV) {
+                    p.fd_cblocks.divmod(kb0, tap, cb);
+                    if (p.taps == 9) { dr = tap / 3 - 1; ds = tap % 3 - 1; }
+                } else if (AM == LD_CONV_WG) {
+                    int tw_i, r, th_i;
+                    p.fd_tiles_w.divmod(kb0, r, tw_i);
+                    p.fd_tiles_h.divmod(r, pn, th_i);
+                    pw0 = tw_i * p.tw;
+                    ph0 = th_i * p.th;
+                    if (p.taps == 9) { dr = c.tap / 3 - 1; ds = c.tap % 3 - 1; }
+                }
+                const int sgn = p.flip ? -1 : 1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(ptx::smem_u32(&ctl->empty[stage]), phase ^ 1);
                     const uint32_t bar = ptx::smem_u32(&ctl->full[stage]);
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + p.a_bytes;
-                    ptx::mbar_expect_tx(bar, p.tx_bytes);
-                    // conv k-block decode (fwd/dgrad: (tap, channel block); wgrad: pixel patch)
-                    int tap = 0, cb = kb, dr = 0, ds = 0, pn = 0, ph0 = 0, pw0 = 0;
-                    if (p.a_mode == TRIS_OP_CONV) {
-                        if (!p.wgrad) {
-                            tap = kb / p.cblocks;
-                            cb = kb - tap * p.cblocks;
-                            if (p.taps == 9) {
-                                dr = tap / 3 - 1;
-                                ds = tap % 3 - 1;
-                                if (p.flip) { dr = -dr; ds = -ds; }
+                    if (p.dbg & 1) {
+                        ptx::mbar_arrive(bar);
+                    } else if (is_a) {
+                        ptx::mbar_expect_tx(bar, p.a_tx);
+                        if (AM == LD_K2D) {
+                            if (p.a_batched) ptx::tma_load_3d(sa, &map_a, bar, kb * 64, m0, c.batch);
+                            else ptx::tma_load_2d(sa, &map_a, bar, kb * 64, m0);
+                        } else if (AM == LD_MN2D) {
+                            if (p.a_batched) {
+                                ptx::tma_load_3d(sa, &map_a, bar, m0, kb * p.bk, c.batch);
+                                ptx::tma_load_3d(sa + p.a_atom, &map_a, bar, m0 + 64, kb * p.bk, c.batch);
+                            } else {
+                                ptx::tma_load_2d(sa, &map_a, bar, m0, kb * p.bk);
+                                ptx::tma_load_2d(sa + p.a_atom, &map_a, bar, m0 + 64, kb * p.bk);
                             }
+                        } else if (AM == LD_CONV) {
+                            ptx::tma_load_4d(sa, &map_a, bar, cb * 64, c.w0 + sgn * ds, c.h0 + sgn * dr, c.n_i);
                         } else {
-                            int tw_i = kb % p.tiles_w;
-                            int r = kb / p.tiles_w;
-                            pw0 = tw_i * p.tw;
-                            ph0 = (r % p.tiles_h) * p.th;
-                            pn = r / p.tiles_h;
-                            if (p.taps == 9) { dr = c.tap / 3 - 1; ds = c.tap % 3 - 1; }
+                            ptx::tma_load_4d(sa, &map_a, bar, m0, pw0, ph0, pn);
+                            ptx::tma_load_4d(sa + p.a_atom, &map_a, bar, m0 + 64, pw0, ph0, pn);
+                        }
+                    } else {
+                        ptx::mbar_expect_tx(bar, p.b_tx);
+                        if (BM == LD_K2D) {
+                            if (p.b_batched) ptx::tma_load_3d(sb, &map_b, bar, kb * 64, n0, c.batch);
+                            else ptx::tma_load_2d(sb, &map_b, bar, kb * 64, n0);
+                        } else if (BM == LD_MN2D) {
+                            for (int j = 0; j < p.bn / 64; ++j) {
+                                if (p.b_batched) ptx::tma_load_3d(sb + j * p.b_atom, &map_b, bar, n0 + 64 * j, kb * p.bk, c.batch);
+                                else ptx::tma_load_2d(sb + j * p.b_atom, &map_b, bar, n0 + 64 * j, kb * p.bk);
+                            }
+                        } else if (BM == LD_MN2D_TAPS) {
+                            const int inner = tap * p.b_tap_stride + n0;
+                            for (int j = 0; j < p.bn / 64; ++j)
+                                ptx::tma_load_2d(sb + j * p.b_atom, &map_b, bar, inner + 64 * j, cb * 64);
+                        } else {
+                            for (int j = 0; j < p.bn / 64; ++j)
+                                ptx::tma_load_4d(sb + j * p.b_atom, &map_b, bar, n0 + 64 * j, pw0 + ds, ph0 + dr, pn);
                         }
                     }
-                    // ---- A
-                    if (p.a_mode == TRIS_OP_K2D) {
-                        ptx::tma_load_2d(sa, &map_a, bar, kb * 64, m0);
-                    } else if (p.a_mode == TRIS_OP_MN2D) {
-                        ptx::tma_load_2d(sa, &map_a, bar, m0, kb * p.bk);
-                        ptx::tma_load_2d(sa + p.a_atom, &map_a, bar, m0 + 64, kb * p.bk);
-                    } else if (!p.wgrad) {
-                        ptx::tma_load_4d(sa, &map_a, bar, cb * 64, c.w0 + ds, c.h0 + dr, c.n_i);
-                    } else {
-                        ptx::tma_load_4d(sa, &map_a, bar, m0, pw0, ph0, pn);
-                        ptx::tma_load_4d(sa + p.a_atom, &map_a, bar, m0 + 64, pw0, ph0, pn);
-                    }
-                    // ---- B
-                    if (p.b_mode == TRIS_OP_K2D) {
-                        ptx::tma_load_2d(sb, &map_b, bar, kb * 64, n0);
-                    } else if (p.b_mode == TRIS_OP_MN2D) {
-                        int inner = n0, outer = kb * p.bk;
-                        if (p.a_mode == TRIS_OP_CONV) { inner = tap * p.b_tap_stride + n0; outer = cb * 64; }
-                        for (int j = 0; j < p.bn / 64; ++j)
-                            ptx::tma_load_2d(sb + j * p.b_atom, &map_b, bar, inner + 64 * j, outer);
-                    } else {
-                        for (int j = 0; j < p.bn / 64; ++j)
-                            ptx::tma_load_4d(sb + j * p.b_atom, &map_b, bar, n0 + 64 * j, pw0 + ds, ph0 + dr, pn);
+                    if (AM == LD_CONV) {
+                        if (++cb == p.cblocks) {
+                            cb = 0;
+                            ++tap;
+                            if (++ds == 2) { ds = -1; ++dr; }
+                        }
+                    } else if (AM == LD_CONV_WG) {
+                        pw0 += p.tw;
+                        if (pw0 >= p.tiles_w * p.tw) {
+                            pw0 = 0;
+                            ph0 += p.th;
+                            if (ph0 >= p.tiles_h * p.th) { ph0 = 0; ++pn; }
+                        }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -205,64 +249,89 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ------------------------------------------------------------------ UMMA issuer (single thread)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            uint32_t acc_phase[2] = {0, 0};
+            uint32_t acc_phase = 0;   // bit b = phase of accumulator buffer b
             int it = 0;
-            const bool a_mn = (p.a_mode == TRIS_OP_MN2D) || (p.a_mode == TRIS_OP_CONV && p.wgrad);
-            const bool b_mn = (p.b_mode != TRIS_OP_K2D);
-            const uint32_t a_kstep = a_mn ? 2048u : 32u, b_kstep = b_mn ? 2048u : 32u;
-            const uint32_t a_lbo = a_mn ? p.a_atom : 0u, b_lbo = b_mn ? p.b_atom : 0u;
+            constexpr bool a_mn = (AM == LD_MN2D) || (AM == LD_CONV_WG);
+            constexpr bool b_mn = (BM != LD_K2D);
+            constexpr uint32_t a_kstep = (a_mn ? 2048u : 32u) >> 4, b_kstep = (b_mn ? 2048u : 32u) >> 4;
+            // descriptor templates: only the 14-bit start-address field changes per stage / k-step
+            const uint64_t da0 = ptx::umma_smem_desc_sw128(0, a_mn ? p.a_atom : 0u, 1024);
+            const uint64_t db0 = ptx::umma_smem_desc_sw128(0, b_mn ? p.b_atom : 0u, 1024);
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const TileCoord c = decode_tile(p, t);
                 const int kb0 = c.split * p.kb_per_split;
                 const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-                const int buf = it & 1;
-                ptx::mbar_wait(ptx::smem_u32(&ctl->acc_empty[buf]), acc_phase[buf] ^ 1);
-                acc_phase[buf] ^= 1;
+                const int buf = it & (p.nacc - 1);
+                if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[2 * 64 + it] = clock64();
+                ptx::mbar_wait(ptx::smem_u32(&ctl->acc_empty[buf]), ((acc_phase >> buf) & 1) ^ 1);
+                if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[3 * 64 + it] = clock64();
+                acc_phase ^= 1u << buf;
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * kAccStride;
+                const uint32_t tmem_d = tmem_base + buf * p.acc_stride;
+                uint32_t accum = 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(ptx::smem_u32(&ctl->full[stage]), phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint32_t sb = sa + p.a_bytes;
-                    for (int k = 0; k < p.n_mma; ++k) {
-                        const uint64_t da = ptx::umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-                        const uint64_t db = ptx::umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-                        ptx::umma_f16(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    const uint32_t sa = (smem_base + stage * stage_bytes) >> 4;
+                    const uint32_t sb = sa + (p.a_bytes >> 4);
+#pragma unroll 4
+                    for (int k = 0; k < ((p.dbg & 2) ? 0 : p.n_mma); ++k) {
+                        ptx::umma_f16(tmem_d, da0 | static_cast<uint64_t>(sa + k * a_kstep), db0 | static_cast<uint64_t>(sb + k * b_kstep),
+                                      p.idesc, accum);
+                        accum = 1;
                     }
-                    ptx::umma_commit(ptx::smem_u32(&ctl->empty[stage]));
+                    if (p.dbg & 16) ptx::mbar_arrive(ptx::smem_u32(&ctl->empty[stage]));
+                    else ptx::umma_commit(ptx::smem_u32(&ctl->empty[stage]));
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(ptx::smem_u32(&ctl->acc_full[buf]));
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    } else if (warp >= 2 && warp < 10) {
+        // ------------------------------------------------------------------ epilogue: 8 warps.  Warp w may touch TMEM
+        // lanes 32*(w%4)..+31; the two warps of a lane quadrant split the 32-column chunks (even / odd).  Values are
+        // staged in 128B-swizzled smem ([group of 128 B columns][128 rows]) and leave through TMA stores (coalesced,
+        // edge-clipped; fp32 weight gradients use TMA reduce-add instead of atomics).
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int tid_e = threadIdx.x - 64;
         const int row = q * 32 + lane;
-        uint32_t acc_phase[2] = {0, 0};
+        const uint32_t stg0 = smem_base + p.stages * stage_bytes;
+        float* s_stats = reinterpret_cast<float*>(smem + p.stages * stage_bytes + p.nstg * p.staging_bytes);
+        const int esz = p.out_f32 ? 4 : 2;
+        const int gw = 128 / esz;                      // columns per 128-byte staging group
+        const int ngroups = (p.bn * esz) / 128;
+        if (p.stats != nullptr) {
+            for (int i = tid_e; i < 2 * p.N; i += 256) s_stats[i] = 0.f;
+        }
+        // statistics mapping (tile-invariant): thread = (16-byte vector of 8 columns, row part)
+        const int nvec = p.bn >> 3;
+        const int vec = tid_e % nvec, part = tid_e / nvec, nparts = 256 / nvec;
+        const int rpp = kBlockM / nparts;
+        uint32_t acc_phase = 0;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const TileCoord c = decode_tile(p, t);
-            const int buf = it & 1;
+            const int buf = it & (p.nacc - 1);
+            const uint32_t stg = stg0 + (p.nstg == 2 ? (it & 1) * p.staging_bytes : 0);
             const int n0 = c.n_t * p.bn;
-            // output row of this thread
-            long grow;
-            bool rvalid;
-            if (p.a_mode == TRIS_OP_CONV && !p.wgrad) {
-                const int hh = c.h0 + row / p.tw, ww = c.w0 + row % p.tw;
-                rvalid = (row < p.th * p.tw) && hh < p.img_h && ww < p.img_w;
-                grow = (static_cast<long>(c.n_i) * p.img_h + hh) * p.img_w + ww;
-            } else {
-                grow = static_cast<long>(c.m_t) * kBlockM + row;
-                rvalid = grow < p.M;
+            const long grow = static_cast<long>(c.m_t) * kBlockM + row;   // plain-mode row (residual / d_pre / dact)
+            const bool rvalid = grow < p.M;
+            // One thread polls the mbarrier (256 pollers would saturate the SM's barrier unit and slow the producer /
+            // issuer threads); the named barrier then releases the other epilogue warps.
+            if (tid_e == 0) {
+                if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[4 * 64 + it] = clock64();
+                ptx::mbar_wait(ptx::smem_u32(&ctl->acc_full[buf]), (acc_phase >> buf) & 1);
+                if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[5 * 64 + it] = clock64();
+                // the TMA stores that last used this staging buffer have finished reading it
+                if (p.nstg == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0();
             }
-            const int col_base = (p.wgrad ? c.tap * p.N : 0) + n0;
-            ptx::mbar_wait(ptx::smem_u32(&ctl->acc_full[buf]), acc_phase[buf]);
-            acc_phase[buf] ^= 1;
+            acc_phase ^= 1u << buf;
+            ptx::named_bar_sync(1, 256);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride;
-            for (int ch = 0; ch < p.bn / 32; ++ch) {
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
+            for (int ch = half; ch < ((p.dbg & 4) ? 0 : p.bn / 32); ch += 2) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(taddr + ch * 32, raw);
                 ptx::tmem_ld_wait();
@@ -276,25 +345,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     for (int i = 0; i < 32; ++i)
                         if (ncol0 + i < p.N) v[i] += __ldg(p.bias + ncol0 + i);
                 }
-                if (p.stats != nullptr) {
-                    float s1[32], s2[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = rvalid ? v[i] : 0.f;
-                        s1[i] = x;
-                        s2[i] = x * x;
-                    }
-                    const float c1 = warp_column_sums(s1, lane);
-                    const float c2 = warp_column_sums(s2, lane);
-                    if (ncol0 + static_cast<int>(lane) < p.N) {
-                        atomicAdd(p.stats + ncol0 + lane, c1);
-                        atomicAdd(p.stats + p.N + ncol0 + lane, c2);
-                    }
-                }
-                // per-thread predicate from here on: no warp-collective ops inside (tcgen05.ld is .sync.aligned)
-                if (rvalid) {
-                const long off = grow * p.ldd + col_base + ch * 32;
-                if (p.d_pre != nullptr) {
+                const long off = grow * p.ldd + ncol0;
+                if (p.d_pre != nullptr && rvalid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (ncol0 + g * 8 < p.N) {
@@ -308,17 +360,19 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                 }
                 if (p.dact_src != nullptr) {
-                    const uint4* sp = reinterpret_cast<const uint4*>(p.dact_src + off);
+                    if (rvalid) {
+                        const uint4* sp = reinterpret_cast<const uint4*>(p.dact_src + off);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (ncol0 + g * 8 < p.N) {
-                            uint4 rr = __ldg(sp + g);
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+                        for (int g = 0; g < 4; ++g) {
+                            if (ncol0 + g * 8 < p.N) {
+                                uint4 rr = __ldg(sp + g);
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(r2[j]);
-                                v[g * 8 + 2 * j] *= act_grad(f.x, p.act);
-                                v[g * 8 + 2 * j + 1] *= act_grad(f.y, p.act);
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = __bfloat1622float2(r2[j]);
+                                    v[g * 8 + 2 * j] *= act_grad(f.x, p.act);
+                                    v[g * 8 + 2 * j + 1] *= act_grad(f.y, p.act);
+                                }
                             }
                         }
                     }
@@ -326,7 +380,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
                 }
-                if (p.residual != nullptr) {
+                if (p.residual != nullptr && rvalid) {
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -342,39 +396,105 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                 }
+                // ---- stage (swizzle: 16-byte chunk index ^ (row & 7), the TMA SWIZZLE_128B pattern)
                 if (p.out_f32) {
-                    float* dp = reinterpret_cast<float*>(p.d) + off;
-                    if (p.atomic) {
+                    const uint32_t base = stg + ch * 16384 + row * 128;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (ncol0 + i < p.N) atomicAdd(dp + i, v[i]);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            if (ncol0 + g * 4 < p.N)
-                                reinterpret_cast<float4*>(dp)[g] =
-                                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        ptx::st_shared_v4(base + ((j ^ (row & 7)) << 4), raw_bits(v[4 * j]), raw_bits(v[4 * j + 1]),
+                                          raw_bits(v[4 * j + 2]), raw_bits(v[4 * j + 3]));
                 } else {
-                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
+                    const uint32_t base = stg + (ch >> 1) * 16384 + row * 128;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (ncol0 + g * 8 < p.N) {
-                            uint4 o;
-                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                o2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-                            reinterpret_cast<uint4*>(dp)[g] = o;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const int idx = (ch & 1) * 4 + j;
+                        ptx::st_shared_v4(base + ((idx ^ (row & 7)) << 4), pack_bf16(v[8 * j], v[8 * j + 1]),
+                                          pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                                          pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
-                }  // rvalid
-                __syncwarp();
             }
+            // accumulator buffer is free for the MMA warp as soon as every epilogue warp has read its part
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->acc_empty[buf]));
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(1, 256);
+            // ---- BatchNorm column statistics of the stored (bf16-rounded) tile.  Thread = (16-byte vector of 8 columns,
+            // row part): one LDS.128 + 3 instructions per element; parts are combined through a 16 KB scratch and the
+            // per-CTA totals live in smem until the kernel ends (one global atomic per column per CTA).
+            if (p.stats != nullptr && !(p.dbg & 4)) {
+                int rlim = kBlockM;
+                constexpr bool conv_tile = (AM == LD_CONV);
+                if (conv_tile) rlim = p.th * p.tw;
+                else rlim = min(kBlockM, p.M - c.m_t * kBlockM);
+                float sa[8], sq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sa[i] = sq[i] = 0.f;
+                const int r0 = part * rpp, r1 = min(rlim, r0 + rpp);
+                int hh = 0, ww = 0;
+                if (conv_tile) { int qh, qw; p.fd_tw.divmod(r0, qh, qw); hh = c.h0 + qh; ww = c.w0 + qw; }
+                const uint32_t gbase = stg + (vec >> 3) * 16384;
+                const int idx = vec & 7;
+                for (int r = r0; r < r1; ++r) {
+                    // patch rows that overhang the image are computed (halo taps see real pixels) but never stored
+                    const bool ok = !conv_tile || (hh < p.img_h && ww < p.img_w);
+                    if (conv_tile && ++ww == c.w0 + p.tw) { ww = c.w0; ++hh; }
+                    if (!ok) continue;
+                    uint32_t w4[4];
+                    ptx::ld_shared_v4(gbase + r * 128 + ((idx ^ (r & 7)) << 4), w4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float x0 = __uint_as_float(w4[k] << 16), x1 = __uint_as_float(w4[k] & 0xffff0000u);
+                        sa[2 * k] += x0; sq[2 * k] = fmaf(x0, x0, sq[2 * k]);
+                        sa[2 * k + 1] += x1; sq[2 * k + 1] = fmaf(x1, x1, sq[2 * k + 1]);
+                    }
+                }
+                float* scr = s_stats + 2 * p.N;                    // [nparts][2][bn]
+                float* dst = scr + (part * 2) * p.bn + vec * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { dst[i] = sa[i]; dst[p.bn + i] = sq[i]; }
+                ptx::named_bar_sync(1, 256);
+                for (int jx = tid_e; jx < 2 * p.bn; jx += 256) {
+                    int which, col;
+                    p.fd_bn.divmod(jx, which, col);
+                    if (n0 + col < p.N) {
+                        float tot = 0.f;
+                        for (int pp = 0; pp < nparts; ++pp) tot += scr[(pp * 2 + which) * p.bn + col];
+                        s_stats[which * p.N + n0 + col] += tot;      // single owner per column within the CTA
+                    }
+                }
+            }
+            if ((p.dbg & 8) && blockIdx.x == 0 && tid_e == 0 && it < 64) p.dbg_buf[6 * 64 + it] = clock64();
+            // ---- TMA store (one elected thread)
+            if (tid_e == 0 && !(p.dbg & 4)) {
+                for (int g = 0; g < ngroups; ++g) {
+                    const int cg = n0 + g * gw;
+                    if (cg >= p.N) break;
+                    const uint32_t src = stg + g * 16384;
+                    if (AM == LD_CONV) {
+                        ptx::tma_store_4d(&map_d, src, cg, c.w0, c.h0, c.n_i);
+                    } else if (p.wgrad) {
+                        ptx::tma_reduce_add_3d(&map_d, src, cg, c.tap, c.m_t * kBlockM);
+                    } else if (p.batch > 1) {
+                        if (p.atomic) ptx::tma_reduce_add_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
+                        else ptx::tma_store_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
+                    } else if (p.atomic) {
+                        ptx::tma_reduce_add_2d(&map_d, src, cg, c.m_t * kBlockM);
+                    } else {
+                        ptx::tma_store_2d(&map_d, src, cg, c.m_t * kBlockM);
+                    }
+                }
+                ptx::bulk_commit();
+            }
+        }
+        if (tid_e == 0) ptx::bulk_wait_all();
+        if (p.stats != nullptr) {
+            ptx::named_bar_sync(1, 256);
+            for (int i = tid_e; i < 2 * p.N; i += 256) {
+                const float sv = s_stats[i];
+                if (sv != 0.f) atomicAdd(p.stats + i, sv);
+            }
         }
     }
     ptx::tc_fence_before();
@@ -395,7 +515,7 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (g->M <= 0 || g->N <= 0 || g->K <= 0) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: empty extent M=%d N=%d K=%d", g->M, g->N, g->K);
     const int bn = g->block_n;
     if (bn < 32 || bn > 256 || bn % 32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: block_n %d not in {32..256 step 32}", bn);
-    if (g->N % 8 || g->ldd % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: N=%d and ldd=%d must be multiples of 8", g->N, g->ldd);
+    if (g->N % 8 || g->ldd % 4) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: N=%d and ldd=%d must be multiples of 8", g->N, g->ldd);
     const bool conv = g->a_mode == TRIS_OP_CONV;
     const bool wgrad = conv && g->wgrad;
     const bool b_mn = g->b_mode != TRIS_OP_K2D;
@@ -405,7 +525,19 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (g->split_k > 1 && !g->atomic) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: split_k needs atomic output");
     if (g->residual && g->out_dtype == TRIS_DT_F32 && g->atomic) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: residual+atomic");
 
+    const int batch = g->batch > 1 ? g->batch : 1;
+    if (batch > 1 && (conv || g->residual || g->d_pre || g->dact_src || g->stats))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: batched form supports the 2-D modes with bias/activation only");
     KParams p{};
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("TRIS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+        p.dbg_buf = nullptr;
+    }
+    p.batch = batch;
+    p.a_batched = batch > 1 && g->a_batch_stride != 0;
+    p.b_batched = batch > 1 && g->b_batch_stride != 0;
     p.M = g->M; p.N = g->N; p.K = g->K;
     p.a_mode = g->a_mode; p.b_mode = g->b_mode; p.wgrad = wgrad; p.flip = g->flip; p.taps = g->taps > 0 ? g->taps : 1;
     p.bn = bn;
@@ -457,15 +589,41 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     // bytes actually delivered per stage (full boxes, OOB elements are zero-filled and counted)
     uint32_t a_tx = p.a_bytes, b_tx = p.b_bytes;
     if (conv && !wgrad) a_tx = p.th * p.tw * 128;
-    p.tx_bytes = a_tx + b_tx;
+    p.a_tx = a_tx;
+    p.b_tx = b_tx;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const uint32_t budget = 227 * 1024 - 1024 - sizeof(SmemCtl) - 64;
+    const bool out_f32 = g->out_dtype == TRIS_DT_F32;
+    if (out_f32 && bn > 128) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: fp32 output needs block_n <= 128 (staging)");
+    if (conv && !wgrad && out_f32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: conv forward/dgrad output is bf16");
+    if (conv && (g->residual || g->d_pre || g->dact_src || g->bias))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: bias/residual/d_pre/dact epilogues are for the 2-D modes");
+    if (wgrad && !out_f32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: weight gradients are fp32");
+    if (g->stats && (out_f32 || g->N > 2048)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stats need bf16 output, N <= 2048");
+    p.staging_bytes = bn * (out_f32 ? 4 : 2) * 128;
+    if (p.staging_bytes < 16384) p.staging_bytes = 16384;
+    p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 + 16384 : 0;
+    p.nacc = 512 / bn >= 4 ? 4 : 2;   // power of two (ring index = it & (nacc - 1))
+    p.acc_stride = bn;
+    const uint32_t fixed = 1024 + sizeof(SmemCtl) + 64 + p.stats_bytes;
+    // two staging buffers (store of tile i overlaps the epilogue of tile i+1) when >= 4 pipeline stages still fit
+    p.nstg = (227 * 1024 - fixed - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
+    const uint32_t budget = 227 * 1024 - fixed - p.nstg * p.staging_bytes;
     p.stages = budget / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
+    { const char* e = getenv("TRIS_GEMM_STAGES"); if (e && atoi(e) >= 2 && (uint32_t)atoi(e) < p.stages) p.stages = atoi(e); }
     if (p.stages < 2) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stage too large (%u bytes)", stage_bytes);
-    const size_t smem_bytes = 1024 + p.stages * stage_bytes + sizeof(SmemCtl) + 64;
+    const size_t smem_bytes = fixed + p.stages * stage_bytes + p.nstg * p.staging_bytes;
 
+    p.fd_tiles_n = make_fastdiv(p.tiles_n); p.fd_tiles_m = make_fastdiv(p.tiles_m); p.fd_tiles_tap = make_fastdiv(p.tiles_tap);
+    p.fd_split = make_fastdiv(p.split_k); p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
+    p.fd_cblocks = make_fastdiv(p.cblocks > 0 ? p.cblocks : 1); p.fd_tw = make_fastdiv(p.tw > 0 ? p.tw : 1); p.fd_bn = make_fastdiv(bn);
     p.idesc = ptx::umma_idesc(1u, a_mn ? 1u : 0u, b_mn ? 1u : 0u, kBlockM, bn);
+    if (p.dbg & 8) {
+        static long long* buf = nullptr;
+        if (!buf) { const char* e = getenv("TRIS_GEMM_DBGBUF"); buf = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+        p.dbg_buf = buf;
+        if (!buf) p.dbg &= ~8;
+    }
     p.d = g->d; p.bias = g->bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual); p.stats = g->stats;
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
@@ -482,16 +640,16 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
         ma = tris::tensor_map_bf16(g->a, 4, dims, str, box);
     } else if (g->a_mode == TRIS_OP_K2D) {
         if (g->lda % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: lda %d %% 8", g->lda);
-        uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->M};
-        uint64_t str[1] = {(uint64_t)g->lda * 2};
-        uint32_t box[2] = {64, kBlockM};
-        ma = tris::tensor_map_bf16(g->a, 2, dims, str, box);
+        uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->M, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)g->lda * 2, (uint64_t)g->a_batch_stride * 2};
+        uint32_t box[3] = {64, kBlockM, 1};
+        ma = tris::tensor_map_bf16(g->a, p.a_batched ? 3 : 2, dims, str, box);
     } else {
         if (g->lda % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: lda %d %% 8", g->lda);
-        uint64_t dims[2] = {(uint64_t)g->M, (uint64_t)g->K};
-        uint64_t str[1] = {(uint64_t)g->lda * 2};
-        uint32_t box[2] = {64, (uint32_t)p.bk};
-        ma = tris::tensor_map_bf16(g->a, 2, dims, str, box);
+        uint64_t dims[3] = {(uint64_t)g->M, (uint64_t)g->K, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)g->lda * 2, (uint64_t)g->a_batch_stride * 2};
+        uint32_t box[3] = {64, (uint32_t)p.bk, 1};
+        ma = tris::tensor_map_bf16(g->a, p.a_batched ? 3 : 2, dims, str, box);
     }
     if (!ma) return TRIS_ERR_SHAPE;
     if (g->b_mode == TRIS_OP_CONV) {
@@ -503,32 +661,70 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
         mb = tris::tensor_map_bf16(g->b, 4, dims, str, box);
     } else if (g->b_mode == TRIS_OP_K2D) {
         if (g->ldb % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: ldb %d %% 8", g->ldb);
-        uint64_t dims[2] = {(uint64_t)g->K, (uint64_t)g->N};
-        uint64_t str[1] = {(uint64_t)g->ldb * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
-        mb = tris::tensor_map_bf16(g->b, 2, dims, str, box);
+        uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->N, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)g->ldb * 2, (uint64_t)g->b_batch_stride * 2};
+        uint32_t box[3] = {64, (uint32_t)bn, 1};
+        mb = tris::tensor_map_bf16(g->b, p.b_batched ? 3 : 2, dims, str, box);
     } else {
         if (g->ldb % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: ldb %d %% 8", g->ldb);
         // [K rows, ldb] row-major; for a conv dgrad the contiguous dim holds taps x N.
         const uint64_t inner = (conv && !wgrad) ? (uint64_t)p.taps * g->b_tap_stride : (uint64_t)g->N;
         const uint64_t outer = (conv && !wgrad) ? (uint64_t)a_ch : (uint64_t)g->K;
-        uint64_t dims[2] = {inner, outer};
-        uint64_t str[1] = {(uint64_t)g->ldb * 2};
-        uint32_t box[2] = {64, (uint32_t)p.bk};
-        mb = tris::tensor_map_bf16(g->b, 2, dims, str, box);
+        uint64_t dims[3] = {inner, outer, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)g->ldb * 2, (uint64_t)g->b_batch_stride * 2};
+        uint32_t box[3] = {64, (uint32_t)p.bk, 1};
+        mb = tris::tensor_map_bf16(g->b, p.b_batched ? 3 : 2, dims, str, box);
     }
     if (!mb) return TRIS_ERR_SHAPE;
-
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRIS_CUDA_OK(cudaFuncSetAttribute(tris_umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    // ---- output tensor map (TMA store / reduce-add, 128-byte swizzled staging groups)
+    const CUtensorMap* md = nullptr;
+    {
+        const int esz = out_f32 ? 4 : 2;
+        if ((g->ldd * esz) % 16) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: ldd %d not 16-byte aligned", g->ldd);
+        if (conv && !wgrad) {
+            uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)p.img_w, (uint64_t)p.img_h, (uint64_t)p.img_n};
+            uint64_t str[3] = {(uint64_t)g->ldd * 2, (uint64_t)p.img_w * g->ldd * 2, (uint64_t)p.img_h * p.img_w * g->ldd * 2};
+            uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+            md = tris::tensor_map_bf16(g->d, 4, dims, str, box, 2);
+        } else if (wgrad) {
+            uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)p.taps, (uint64_t)g->M};
+            uint64_t str[2] = {(uint64_t)g->N * 4, (uint64_t)g->ldd * 4};
+            uint32_t box[3] = {32, 1, (uint32_t)kBlockM};
+            md = tris::tensor_map_bf16(g->d, 3, dims, str, box, 4);
+        } else {
+            uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)batch};
+            uint64_t str[2] = {(uint64_t)g->ldd * esz, (uint64_t)g->d_batch_stride * esz};
+            uint32_t box[3] = {(uint32_t)(128 / esz), (uint32_t)kBlockM, 1};
+            if (batch > 1 && ((g->d_batch_stride * esz) % 16 || g->d_batch_stride == 0))
+                return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: d_batch_stride must be non-zero and 16-byte aligned");
+            md = tris::tensor_map_bf16(g->d, batch > 1 ? 3 : 2, dims, str, box, esz);
+        }
     }
-    const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k;
+    if (!md) return TRIS_ERR_SHAPE;
+
+    int am = LD_K2D, bm = LD_K2D;
+    if (conv && !wgrad) am = LD_CONV; else if (wgrad) am = LD_CONV_WG; else if (g->a_mode == TRIS_OP_MN2D) am = LD_MN2D;
+    if (wgrad) bm = LD_CONV_WG; else if (g->b_mode == TRIS_OP_MN2D) bm = (conv ? LD_MN2D_TAPS : LD_MN2D);
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+    KernelFn fn = nullptr;
+    if (am == LD_K2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_K2D, LD_K2D>;
+    else if (am == LD_K2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_K2D, LD_MN2D>;
+    else if (am == LD_MN2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_MN2D>;
+    else if (am == LD_MN2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_K2D>;
+    else if (am == LD_CONV && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_CONV, LD_K2D>;
+    else if (am == LD_CONV && bm == LD_MN2D_TAPS) fn = tris_umma_gemm_kernel<LD_CONV, LD_MN2D_TAPS>;
+    else if (am == LD_CONV_WG && bm == LD_CONV_WG) fn = tris_umma_gemm_kernel<LD_CONV_WG, LD_CONV_WG>;
+    else return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: unsupported operand mode combination a=%d b=%d", g->a_mode, g->b_mode);
+    static bool attr_set[8][8] = {};
+    if (!attr_set[am][bm]) {
+        TRIS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[am][bm] = true;
+    }
+    const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k * p.batch;
     int ctas = tris::sm_count();
     if (g->max_ctas > 0 && g->max_ctas < ctas) ctas = g->max_ctas;
     if (total_tiles < ctas) ctas = total_tiles;
-    tris_umma_gemm_kernel<<<ctas, kThreads, smem_bytes, stream>>>(*ma, *mb, p);
+    fn<<<ctas, kThreads, smem_bytes, stream>>>(*ma, *mb, *md, p);
     TRIS_LAUNCH_OK("tris_umma_gemm_kernel");
     return TRIS_OK;
 }

@@ -59,7 +59,31 @@ __global__ void embed_bwd_kernel(const int* __restrict__ ids, const __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------------- LayerNorm (one warp per row)
-template <int MAXV>  // D <= MAXV * 32 * 8 ... we keep per-lane values in registers: D/32 floats per lane
+// 128-bit loads: lane handles vectors lane, lane+32, ... of 8 bf16 (D % 256 == 0: 512 -> 2, 768 -> 3, 1024 -> 4 per lane)
+struct V8 { float v[8]; };
+__device__ __forceinline__ V8 ldv8(const __nv_bfloat16* p) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); o.v[2 * j] = f.x; o.v[2 * j + 1] = f.y; }
+    return o;
+}
+__device__ __forceinline__ void stv8(__nv_bfloat16* p, const V8& x) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(x.v[2 * j], x.v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ V8 ldf8(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    V8 o;
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+    return o;
+}
+
+template <int NV>   // vectors per lane = D / 256
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -68,34 +92,36 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const __nv_bfloat16* xr = x + static_cast<long>(row) * D;
-    float v[MAXV];
+    V8 v[NV];
     float s = 0.f;
-    const int per = D / 32;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        if (i < per) {
-            v[i] = __bfloat162float(xr[i * 32 + lane]);
-            s += v[i];
-        }
+    for (int i = 0; i < NV; ++i) {
+        v[i] = ldv8(xr + (i * 32 + lane) * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i].v[j];
     }
     const float mean = warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-        if (i < per) { const float d = v[i] - mean; q += d * d; }
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i].v[j] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) / D + eps);
     __nv_bfloat16* yr = y + static_cast<long>(row) * D;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-        if (i < per) {
-            const int c = i * 32 + lane;
-            yr[c] = __float2bfloat16((v[i] - mean) * rstd * gamma[c] + beta[c]);
-        }
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        const V8 g = ldf8(gamma + c), b = ldf8(beta + c);
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = (v[i].v[j] - mean) * rstd * g.v[j] + b.v[j];
+        stv8(yr + c, o);
+    }
     if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
 // dx = (add ? add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
-template <int MAXV>
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ add,
@@ -103,49 +129,60 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             float* __restrict__ dbeta, int rows, int D) {
     extern __shared__ float sm[];   // [2*D] block partials of dgamma/dbeta
     const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per = D / 32;
     const bool want_param = dgamma != nullptr;
     if (want_param) {
         for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
         __syncthreads();
     }
-    float pg[MAXV], pb[MAXV];
+    V8 gam[NV], pg[NV], pb[NV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) pg[i] = pb[i] = 0.f;
+    for (int i = 0; i < NV; ++i) {
+        gam[i] = ldf8(gamma + (i * 32 + lane) * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pg[i].v[j] = pb[i].v[j] = 0.f;
+    }
     for (int row = blockIdx.x * warps + wid; row < rows; row += gridDim.x * warps) {
         const long base = static_cast<long>(row) * D;
         const float mean = mean_in[row], rstd = rstd_in[row];
-        float g[MAXV], xh[MAXV];
+        V8 g[NV], xh[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i)
-            if (i < per) {
-                const int c = i * 32 + lane;
-                const float d = __bfloat162float(dy[base + c]);
-                xh[i] = (__bfloat162float(x[base + c]) - mean) * rstd;
-                g[i] = d * gamma[c];
-                s1 += g[i];
-                s2 += g[i] * xh[i];
-                pg[i] += d * xh[i];
-                pb[i] += d;
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            const V8 d = ldv8(dy + base + c), xv = ldv8(x + base + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[i].v[j] = (xv.v[j] - mean) * rstd;
+                g[i].v[j] = d.v[j] * gam[i].v[j];
+                s1 += g[i].v[j];
+                s2 = fmaf(g[i].v[j], xh[i].v[j], s2);
+                pg[i].v[j] = fmaf(d.v[j], xh[i].v[j], pg[i].v[j]);
+                pb[i].v[j] += d.v[j];
             }
+        }
         s1 = warp_sum(s1) / D;
         s2 = warp_sum(s2) / D;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i)
-            if (i < per) {
-                const int c = i * 32 + lane;
-                float o = rstd * (g[i] - s1 - xh[i] * s2);
-                if (add != nullptr) o += __bfloat162float(add[base + c]);
-                dx[base + c] = __float2bfloat16(o);
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = rstd * (g[i].v[j] - s1 - xh[i].v[j] * s2);
+            if (add != nullptr) {
+                const V8 a = ldv8(add + base + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += a.v[j];
             }
+            stv8(dx + base + c, o);
+        }
     }
     if (want_param) {
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i)
-            if (i < per) {
-                atomicAdd(&sm[i * 32 + lane], pg[i]);
-                atomicAdd(&sm[D + i * 32 + lane], pb[i]);
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sm[(i * 32 + lane) * 8 + j], pg[i].v[j]);
+                atomicAdd(&sm[D + (i * 32 + lane) * 8 + j], pb[i].v[j]);
             }
         __syncthreads();
         for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -159,7 +196,80 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 constexpr int HD = 64;
 constexpr int HDP = HD + 1;
 
-// one block (128 threads) per (sequence, head).  qkv: [N*L, 3*D] bf16 (q | k | v), out: [N*L, D]
+// one block (128 threads) per (sequence, head).  qkv: [N*L, 3*D] bf16 (q | k | v), out: [N*L, D].
+// All contractions are 4x4 register tiles (0.5 shared-memory loads per FMA); softmax rows by warp shuffles.
+__device__ __forceinline__ void softmax_rows(float* s, float* ds, int L, bool bwd) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = wid; a < L; a += 4) {
+        float m = -CUDART_INF_F;
+        for (int b = lane; b < L; b += 32) m = fmaxf(m, s[a * (L + 1) + b]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int b = lane; b < L; b += 32) {
+            const float e = __expf(s[a * (L + 1) + b] - m);
+            s[a * (L + 1) + b] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        if (!bwd) {
+            for (int b = lane; b < L; b += 32) s[a * (L + 1) + b] *= inv;
+        } else {
+            float delta = 0.f;
+            for (int b = lane; b < L; b += 32) {
+                const float pr = s[a * (L + 1) + b] * inv;
+                s[a * (L + 1) + b] = pr;
+                delta += pr * ds[a * (L + 1) + b];
+            }
+            delta = warp_sum(delta);
+            for (int b = lane; b < L; b += 32) ds[a * (L + 1) + b] = s[a * (L + 1) + b] * (ds[a * (L + 1) + b] - delta);
+        }
+    }
+}
+
+template <bool BWD>
+__device__ __forceinline__ void score_tiles(const float* q, const float* k, const float* go, const float* v, float* s, float* ds,
+                                            int L, int causal) {
+    const int nt = (L + 3) >> 2;
+    for (int id = threadIdx.x; id < nt * nt; id += blockDim.x) {
+        const int a0 = (id / nt) * 4, b0 = (id % nt) * 4;
+        int ar[4], br[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ar[i] = min(a0 + i, L - 1) * HDP; br[i] = min(b0 + i, L - 1) * HDP; }
+        float acc[4][4], dp[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = dp[i][jj] = 0.f;
+        for (int d = 0; d < HD; ++d) {
+            float qa[4], kb[4], ga[4], vb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { qa[i] = q[ar[i] + d]; kb[i] = k[br[i] + d]; }
+            if (BWD) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ga[i] = go[ar[i] + d]; vb[i] = v[br[i] + d]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    acc[i][jj] = fmaf(qa[i], kb[jj], acc[i][jj]);
+                    if (BWD) dp[i][jj] = fmaf(ga[i], vb[jj], dp[i][jj]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int a = a0 + i, b = b0 + jj;
+                if (a < L && b < L) {
+                    s[a * (L + 1) + b] = (causal && b > a) ? -CUDART_INF_F : acc[i][jj];
+                    if (BWD) ds[a * (L + 1) + b] = (causal && b > a) ? 0.f : dp[i][jj];
+                }
+            }
+    }
+}
+
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                        int L, int heads, int causal) {
     extern __shared__ float sm[];
@@ -178,38 +288,37 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __re
         v[l * HDP + d] = __bfloat162float(r[2 * D]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
-        const int a = i / L, b = i % L;
-        float acc = -CUDART_INF_F;
-        if (!causal || b <= a) {
-            acc = 0.f;
-#pragma unroll 16
-            for (int d = 0; d < HD; ++d) acc += q[a * HDP + d] * k[b * HDP + d];
-        }
-        s[a * (L + 1) + b] = acc;
-    }
+    score_tiles<false>(q, k, nullptr, nullptr, s, nullptr, L, causal);
     __syncthreads();
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int a = wid; a < L; a += 4) {
-        float m = -CUDART_INF_F;
-        for (int b = lane; b < L; b += 32) m = fmaxf(m, s[a * (L + 1) + b]);
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int b = lane; b < L; b += 32) {
-            const float e = __expf(s[a * (L + 1) + b] - m);
-            s[a * (L + 1) + b] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.f / sum;
-        for (int b = lane; b < L; b += 32) s[a * (L + 1) + b] *= inv;
-    }
+    softmax_rows(s, nullptr, L, false);
     __syncthreads();
-    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
-        const int a = i / HD, d = i % HD;
-        float acc = 0.f;
-        for (int b = 0; b < L; ++b) acc += s[a * (L + 1) + b] * v[b * HDP + d];
-        out[(row0 + a) * D + h * HD + d] = __float2bfloat16(acc);
+    const int nta = (L + 3) >> 2;
+    for (int id = threadIdx.x; id < nta * 16; id += blockDim.x) {
+        const int a0 = (id >> 4) * 4, d0 = (id & 15) * 4;
+        int ar[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ar[i] = min(a0 + i, L - 1) * (L + 1);
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.f;
+        for (int b = 0; b < L; ++b) {
+            float pa[4], vb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pa[i] = s[ar[i] + b]; vb[i] = v[b * HDP + d0 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(pa[i], vb[jj], acc[i][jj]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (a0 + i < L) {
+                __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + (row0 + a0 + i) * D + h * HD + d0);
+                o[0] = __floats2bfloat162_rn(acc[i][0], acc[i][1]);
+                o[1] = __floats2bfloat162_rn(acc[i][2], acc[i][3]);
+            }
     }
 }
 
@@ -235,56 +344,55 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const __nv_bfloat16* __re
         go[l * HDP + d] = __bfloat162float(dout[(row0 + l) * D + h * HD + d]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < L * L; i += blockDim.x) {
-        const int a = i / L, b = i % L;
-        float acc = -CUDART_INF_F, dp = 0.f;
-        if (!causal || b <= a) {
-            acc = 0.f;
-#pragma unroll 16
-            for (int d = 0; d < HD; ++d) {
-                acc += q[a * HDP + d] * k[b * HDP + d];
-                dp += go[a * HDP + d] * v[b * HDP + d];
-            }
-        }
-        s[a * (L + 1) + b] = acc;
-        ds[a * (L + 1) + b] = dp;
-    }
+    score_tiles<true>(q, k, go, v, s, ds, L, causal);
     __syncthreads();
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int a = wid; a < L; a += 4) {
-        float m = -CUDART_INF_F;
-        for (int b = lane; b < L; b += 32) m = fmaxf(m, s[a * (L + 1) + b]);
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int b = lane; b < L; b += 32) {
-            const float e = __expf(s[a * (L + 1) + b] - m);
-            s[a * (L + 1) + b] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.f / sum;
-        float delta = 0.f;
-        for (int b = lane; b < L; b += 32) {
-            const float p = s[a * (L + 1) + b] * inv;
-            s[a * (L + 1) + b] = p;
-            delta += p * ds[a * (L + 1) + b];
-        }
-        delta = warp_sum(delta);
-        for (int b = lane; b < L; b += 32) ds[a * (L + 1) + b] = s[a * (L + 1) + b] * (ds[a * (L + 1) + b] - delta);
-    }
+    softmax_rows(s, ds, L, true);
     __syncthreads();
-    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
-        const int a = i / HD, d = i % HD;
-        float dq = 0.f, dk = 0.f, dv = 0.f;
+    const int nta = (L + 3) >> 2;
+    for (int id = threadIdx.x; id < nta * 16; id += blockDim.x) {
+        const int a0 = (id >> 4) * 4, d0 = (id & 15) * 4;
+        int ac[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ac[i] = min(a0 + i, L - 1);
+        float dq[4][4], dk[4][4], dv[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) dq[i][jj] = dk[i][jj] = dv[i][jj] = 0.f;
         for (int b = 0; b < L; ++b) {
-            dq += ds[a * (L + 1) + b] * k[b * HDP + d];
-            dk += ds[b * (L + 1) + a] * q[b * HDP + d];   // q already carries the 1/8 scale
-            dv += s[b * (L + 1) + a] * go[b * HDP + d];
+            float dsa[4], dst[4], pt[4], kb[4], qb[4], gb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dsa[i] = ds[ac[i] * (L + 1) + b];
+                dst[i] = ds[b * (L + 1) + ac[i]];
+                pt[i] = s[b * (L + 1) + ac[i]];
+                kb[i] = k[b * HDP + d0 + i];
+                qb[i] = q[b * HDP + d0 + i];      // q already carries the 1/8 scale
+                gb[i] = go[b * HDP + d0 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    dq[i][jj] = fmaf(dsa[i], kb[jj], dq[i][jj]);
+                    dk[i][jj] = fmaf(dst[i], qb[jj], dk[i][jj]);
+                    dv[i][jj] = fmaf(pt[i], gb[jj], dv[i][jj]);
+                }
         }
-        __nv_bfloat16* r = dqkv + (row0 + a) * 3 * D + h * HD + d;
-        r[0] = __float2bfloat16(dq * 0.125f);
-        r[D] = __float2bfloat16(dk);
-        r[2 * D] = __float2bfloat16(dv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (a0 + i < L) {
+                __nv_bfloat16* r = dqkv + (row0 + a0 + i) * 3 * D + h * HD + d0;
+                __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(r);
+                o[0] = __floats2bfloat162_rn(dq[i][0] * 0.125f, dq[i][1] * 0.125f);
+                o[1] = __floats2bfloat162_rn(dq[i][2] * 0.125f, dq[i][3] * 0.125f);
+                o = reinterpret_cast<__nv_bfloat162*>(r + D);
+                o[0] = __floats2bfloat162_rn(dk[i][0], dk[i][1]);
+                o[1] = __floats2bfloat162_rn(dk[i][2], dk[i][3]);
+                o = reinterpret_cast<__nv_bfloat162*>(r + 2 * D);
+                o[0] = __floats2bfloat162_rn(dv[i][0], dv[i][1]);
+                o[1] = __floats2bfloat162_rn(dv[i][2], dv[i][3]);
+            }
     }
 }
 
@@ -354,24 +462,40 @@ int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, 
 
 int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int rows, int D,
                        float eps, tris_stream_t stream) {
-    if (D % 32 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_fwd: D=%d must be %%32 and <= 1024", D);
+    if (D % 256 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_fwd: D=%d must be a multiple of 256, <= 1024", D);
     const int warps = 8;
-    layernorm_fwd_kernel<32><<<(rows + warps - 1) / warps, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, rows, D, eps);
+    const dim3 grid((rows + warps - 1) / warps);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    switch (D / 256) {
+        case 1: layernorm_fwd_kernel<1><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
+        case 2: layernorm_fwd_kernel<2><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
+        case 3: layernorm_fwd_kernel<3><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
+        default: layernorm_fwd_kernel<4><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
+    }
     TRIS_LAUNCH_OK("layernorm_fwd_kernel");
     return TRIS_OK;
 }
 
 int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* add,
                        void* dx, float* dgamma, float* dbeta, int rows, int D, tris_stream_t stream) {
-    if (D % 32 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: D=%d must be %%32 and <= 1024", D);
+    if (D % 256 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: D=%d must be a multiple of 256, <= 1024", D);
     const int warps = 8;
     int grid = (rows + warps - 1) / warps;
-    const int cap = 2 * tris::sm_count();
+    const int cap = dgamma != nullptr ? tris::sm_count() : 4 * tris::sm_count();   // fewer blocks = fewer global atomics
     if (grid > cap) grid = cap;
-    layernorm_bwd_kernel<32><<<grid, warps * 32, 2 * D * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
-        reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, D);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16*>(dy), *xp = reinterpret_cast<const __nv_bfloat16*>(x),
+                        *ap = reinterpret_cast<const __nv_bfloat16*>(add);
+    __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+    const size_t smb = 2 * D * sizeof(float);
+    switch (D / 256) {
+        case 1: layernorm_bwd_kernel<1><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
+        case 2: layernorm_bwd_kernel<2><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
+        case 3: layernorm_bwd_kernel<3><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
+        default: layernorm_bwd_kernel<4><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
+    }
     TRIS_LAUNCH_OK("layernorm_bwd_kernel");
     return TRIS_OK;
 }

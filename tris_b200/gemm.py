@@ -14,15 +14,21 @@ SMS = 148
 
 
 def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
-    """UMMA N per tile: the widest of 256/128/64 that still yields >= one wave of tiles (148 SMs)."""
+    """UMMA N per tile.  The mainloop is L2->smem bound for narrow tiles (a 128 x BN tile moves (128 + BN) * 128 B per
+    k-block for BN * 128 * 64 MACs), so pick the width that minimises  waves(148 SMs) * (128 + BN)."""
     if n <= 32 and not mn_major_b:
         return 32
     n_pad = ((n + 63) // 64) * 64
-    cands = [bn for bn in (256, 128, 64) if bn <= n_pad] or [64]
-    for bn in cands:
-        if tiles_m * ((n + bn - 1) // bn) >= SMS:
-            return bn
-    return cands[-1]
+    best, best_cost = 64, None
+    for bn in (64, 128, 256):
+        if bn > n_pad and bn != 64:
+            continue
+        tiles = tiles_m * ((n + bn - 1) // bn)
+        waves = (tiles + SMS - 1) // SMS
+        cost = waves * (128 + bn)
+        if best_cost is None or cost <= best_cost:
+            best, best_cost = bn, cost
+    return best
 
 
 def _desc(**kw) -> L.GemmDesc:
@@ -47,6 +53,8 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
         out = torch.empty((m, n), device=x.device, dtype=out_dtype)
     tiles_m = (m + 127) // 128
     bn = block_n or _bn_for(n, tiles_m)
+    if out.dtype == torch.float32:
+        bn = min(bn, 128)
     d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(out), bias=L.ptr(bias), residual=L.ptr(residual), stats=L.ptr(stats),
               a_mode=L.OP_K2D, b_mode=L.OP_K2D, M=m, N=n, K=k, lda=k, ldb=k, ldd=n, taps=1, block_n=bn, split_k=1,
               act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16, d_pre=L.ptr(d_pre))
@@ -65,6 +73,8 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
         out = torch.empty((m, k), device=dy.device, dtype=out_dtype)
     tiles_m = (m + 127) // 128
     bn = block_n or _bn_for(k, tiles_m, True)
+    if out.dtype == torch.float32:
+        bn = min(bn, 128)
     d = _desc(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
               b_mode=L.OP_MN2D, M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1, act=act,
               dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
@@ -86,7 +96,7 @@ def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
     k = x.shape[1]
     assert x.shape[0] == m
     tiles_m = (n + 127) // 128
-    bn = block_n or _bn_for(k, tiles_m, True)
+    bn = min(block_n or _bn_for(k, tiles_m, True), 128)
     tiles = tiles_m * ((k + bn - 1) // bn)
     kblocks = (m + 63) // 64
     sk = split_k or _split_for(tiles, kblocks)
@@ -173,16 +183,38 @@ def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
     th, tw = conv_tile(h, w, max_rows=96, mult=16)
     kblocks = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
     tiles_m = (co + 127) // 128
-    bn = block_n or _bn_for(ci, 9 * tiles_m, True)
+    bn = min(block_n or _bn_for(ci, 9 * tiles_m, True), 128)
     tiles = 9 * tiles_m * ((ci + bn - 1) // bn)
     sk = split_k or _split_for(tiles, kblocks)
-    atomic = 1 if sk > 1 else 0
+    atomic = 1      # the conv weight-gradient epilogue always leaves through TMA reduce-add
     if out is None:
-        out = (torch.zeros if atomic else torch.empty)((co, 9 * ci), device=dy.device, dtype=torch.float32)
-    elif atomic:
+        out = torch.zeros((co, 9 * ci), device=dy.device, dtype=torch.float32)
+    else:
         out.zero_()
     d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_CONV, M=co, N=ci, K=n * h * w,
               ldd=9 * ci, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, wgrad=1, block_n=bn, split_k=sk,
               out_dtype=L.DT_F32, atomic=atomic)
+    L.gemm_raw(d)
+    return out
+
+
+# --------------------------------------------------------------------------------------- generic / batched entry
+def gemm_ex(a, b, out, M, N, K, a_mode=L.OP_K2D, b_mode=L.OP_K2D, lda=None, ldb=None, ldd=None, batch=1, a_bs=0, b_bs=0,
+            d_bs=0, bias=None, act=L.ACT_NONE, atomic=0, split_k=1, block_n=None):
+    """out[b] (M x N, row stride ldd) = act(A[b] . B[b]^T-ish + bias) on explicit extents / strides, so strided views
+    (e.g. the Q/K/V thirds of a fused projection) and per-image batches can be used without copies.
+    a_mode K2D: A[b] is [M, K] rows (stride lda);  MN2D: A[b] is [K, M] rows.   b likewise with N."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    lda = lda if lda is not None else (K if a_mode == L.OP_K2D else M)
+    ldb = ldb if ldb is not None else (K if b_mode == L.OP_K2D else N)
+    ldd = ldd if ldd is not None else N
+    f32 = out.dtype == torch.float32
+    tiles_m = ((M + 127) // 128) * batch
+    bn = block_n or _bn_for(N, tiles_m, b_mode != L.OP_K2D)
+    if f32:
+        bn = min(bn, 128)
+    d = _desc(a=L.ptr(a), b=L.ptr(b), d=L.ptr(out), bias=L.ptr(bias), a_mode=a_mode, b_mode=b_mode, M=M, N=N, K=K, lda=lda,
+              ldb=ldb, ldd=ldd, taps=1, block_n=bn, split_k=split_k, act=act, out_dtype=L.DT_F32 if f32 else L.DT_BF16,
+              atomic=atomic, batch=batch, a_batch_stride=a_bs, b_batch_stride=b_bs, d_batch_stride=d_bs)
     L.gemm_raw(d)
     return out
