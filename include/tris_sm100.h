@@ -79,7 +79,7 @@ typedef struct tris_gemm_desc {
     int32_t batch;        /* >1: `batch` independent GEMMs of extents M,N,K (2-D modes only; per-image products of the
                              cross-modal attention, model/attn.py:118-131).  Rows beyond M / K of one batch entry are
                              zero-filled by TMA, so M and K need not be multiples of the tile */
-    int32_t reserved0;
+    float scale;          /* accumulator scale applied before the bias; 0 is read as 1 (no scaling) */
     int64_t a_batch_stride, b_batch_stride, d_batch_stride; /* elements; 0 for A/B = operand shared by all batches */
 } tris_gemm_desc;
 

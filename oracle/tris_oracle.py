@@ -264,8 +264,8 @@ def stage1_losses(cls_out, sig_out, img, word_ids, neg_word_ids, aux: SD, w1=1.0
         nscore = torch.einsum("bc,bkc->bk", f, nfeat)
         l5 = (-torch.log(1 - nscore)).mean(dim=1).sum() / b                # :345-353
     else:
-        l5 = torch.zeros((), dtype=img.dtype)
-    l4 = F.multilabel_soft_margin_loss(cls_out, torch.eye(b, dtype=cls_out.dtype))  # :354
+        l5 = torch.zeros((), dtype=img.dtype, device=img.device)
+    l4 = F.multilabel_soft_margin_loss(cls_out, torch.eye(b, dtype=cls_out.dtype, device=cls_out.device))  # :354
     return {"loss": l1 * w1 + l4 * w4 + l5 * w5, "l1": l1, "l4": l4, "l5": l5, "fg": fg}
 
 

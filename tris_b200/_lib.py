@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int32), ("split_k", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32),
         ("atomic", C.c_int32), ("max_ctas", C.c_int32),
         ("d_pre", C.c_void_p), ("dact_src", C.c_void_p),
-        ("batch", C.c_int32), ("reserved0", C.c_int32),
+        ("batch", C.c_int32), ("scale", C.c_float),
         ("a_batch_stride", C.c_int64), ("b_batch_stride", C.c_int64), ("d_batch_stride", C.c_int64),
     ]
 

@@ -62,6 +62,7 @@ struct KParams {
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
     int ldd, act, out_f32, atomic;
+    float scale;                     // accumulator scale applied before the bias (1 = none)
 };
 
 struct SmemCtl {
@@ -339,7 +340,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (ncol0 >= p.N) continue;      // warp-uniform
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.scale;
                 if (p.bias != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -515,7 +516,9 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (g->M <= 0 || g->N <= 0 || g->K <= 0) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: empty extent M=%d N=%d K=%d", g->M, g->N, g->K);
     const int bn = g->block_n;
     if (bn < 32 || bn > 256 || bn % 32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: block_n %d not in {32..256 step 32}", bn);
-    if (g->N % 8 || g->ldd % 4) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: N=%d and ldd=%d must be multiples of 8", g->N, g->ldd);
+    // the 16-byte epilogue vectors (bf16 stores, residual / d_pre / dact_src loads) need N % 8; plain fp32 output does not
+    const bool vec_epi = g->out_dtype != TRIS_DT_F32 || g->residual || g->d_pre || g->dact_src;
+    if ((vec_epi && g->N % 8) || g->ldd % 4) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: N=%d (%%8) / ldd=%d (%%4) alignment", g->N, g->ldd);
     const bool conv = g->a_mode == TRIS_OP_CONV;
     const bool wgrad = conv && g->wgrad;
     const bool b_mn = g->b_mode != TRIS_OP_K2D;
@@ -628,6 +631,7 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;
+    p.scale = g->scale == 0.f ? 1.f : g->scale;
 
     // ---- tensor maps
     const CUtensorMap *ma = nullptr, *mb = nullptr;

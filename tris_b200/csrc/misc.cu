@@ -107,6 +107,41 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const __nv_bfloat16* __
     for (int c = lane; c < D; c += 32) y[static_cast<long>(row) * D + c] = __float2bfloat16(__bfloat162float(xr[c]) * inv);
     if (lane == 0) inv_norm[row] = inv;
 }
+// fp32 input variant: also emits the normalised rows in fp32 (input of the per-image centring below).
+__global__ void __launch_bounds__(256) l2norm_fwd_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                             float* __restrict__ y32, float* __restrict__ inv_norm, int rows, int D) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<long>(row) * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = xr[c]; s += v * v; }
+    const float inv = rsqrtf(warp_sum(s));
+    for (int c = lane; c < D; c += 32) {
+        const float v = xr[c] * inv;
+        y[static_cast<long>(row) * D + c] = __float2bfloat16(v);
+        if (y32 != nullptr) y32[static_cast<long>(row) * D + c] = v;
+    }
+    if (lane == 0) inv_norm[row] = inv;
+}
+
+// out (bf16) = x - mean over the P pixels of each image, per channel; x fp32 [B*P, C].  The centring is done in fp32
+// BEFORE the bf16 rounding: the 1x1 convs that consume it are followed by an InstanceNorm (attn.py:72-86), which removes
+// the pixel mean anyway, so feeding the centred tensor is exact -- and keeps the pixel-to-pixel variation of a nearly
+// pixel-constant feature map at full bf16 relative precision.  block = (64 channels, 4 pixel groups), grid = (C/64, B).
+__global__ void __launch_bounds__(256) center_pixels_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int P, int C) {
+    __shared__ float red[4][64];
+    const int c = blockIdx.x * 64 + threadIdx.x, b = blockIdx.y, pg = threadIdx.y;
+    float s = 0.f;
+    for (int p = pg; p < P; p += 4) s += x[(static_cast<long>(b) * P + p) * C + c];
+    red[pg][threadIdx.x] = s;
+    __syncthreads();
+    const float mean = (red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]) / P;
+    for (int p = pg; p < P; p += 4) {
+        const long idx = (static_cast<long>(b) * P + p) * C + c;
+        out[idx] = __float2bfloat16(x[idx] - mean);
+    }
+}
+
 // dx = inv * (dy - y * <dy, y>)
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                          const float* __restrict__ inv_norm, __nv_bfloat16* __restrict__ dx, int rows,
@@ -256,6 +291,20 @@ int tris_l2norm_fwd(const void* x, void* y, float* inv_norm, int rows, int D, tr
     l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), inv_norm, rows, D);
     TRIS_LAUNCH_OK("l2norm_fwd_kernel");
+    return TRIS_OK;
+}
+
+int tris_l2norm_fwd_f32(const float* x, void* y, float* y32, float* inv_norm, int rows, int D, tris_stream_t stream) {
+    l2norm_fwd_f32_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), y32,
+                                                                                              inv_norm, rows, D);
+    TRIS_LAUNCH_OK("l2norm_fwd_f32_kernel");
+    return TRIS_OK;
+}
+
+int tris_center_pixels(const float* x, void* out, int B, int P, int C, tris_stream_t stream) {
+    if (C % 64) return tris::fail(TRIS_ERR_SHAPE, "center_pixels: C=%d %% 64", C);
+    center_pixels_kernel<<<dim3(C / 64, B), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out), P, C);
+    TRIS_LAUNCH_OK("center_pixels_kernel");
     return TRIS_OK;
 }
 

@@ -54,6 +54,7 @@ class _EngineBase:
         st.publish_grads()
         for k in self.extra_grad_keys:
             if st.params[k].grad is None:
+                st.g(k).zero_()
                 st.params[k].grad = st.g(k)
 
 
@@ -72,10 +73,54 @@ class _VitFn(torch.autograd.Function):
 
 
 def patchify(img, ps=32):
-    """[N,3,H,W] -> bf16 [N*(H/ps)*(W/ps), 3*ps*ps] with k = c*ps*ps + py*ps + px (conv1.weight.reshape(W,-1) order)."""
-    n, c, h, w = img.shape
-    gh, gw = h // ps, w // ps
-    return img.reshape(n, c, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5).reshape(n * gh * gw, c * ps * ps).to(bf16).contiguous()
+    """[N,3,S,S] fp32 -> bf16 [N*(S/ps)^2, 3*ps*ps] with k = c*ps*ps + py*ps + px (conv1.weight.reshape(W,-1) order)."""
+    return ops.mask_resize_fwd(None, img.float().contiguous(), out_size=img.shape[2], ps=ps)[0]
+
+
+class _MaskResizeFn(torch.autograd.Function):
+    """fg = bilinear_ac(sig -> 224) * bilinear_ac(img -> 224), emitted as ViT-B/32 patches (train_stage1.py:327-339)."""
+
+    @staticmethod
+    def forward(ctx, sig, img, size, ps):
+        img = img.float().contiguous()
+        patches, _ = ops.mask_resize_fwd(sig.contiguous(), img, size, ps)
+        ctx.img, ctx.size, ctx.ps = img, size, ps
+        return patches
+
+    @staticmethod
+    def backward(ctx, dpatches):
+        return ops.mask_resize_bwd(dpatches.contiguous(), ctx.img, ctx.size, ctx.ps), None, None, None
+
+
+def masked_patches(sig, img, size=224, ps=32):
+    return _MaskResizeFn.apply(sig, img, size, ps)
+
+
+class _LossFn(torch.autograd.Function):
+    """(f [B,512] bf16, g [B*(1+K),512] bf16, cls [B,B] f32) -> (loss, l1, l4, l5); train_stage1.py:340-364."""
+
+    @staticmethod
+    def forward(ctx, f, g, cls, k, w):
+        f, g, cls = f.contiguous(), g.contiguous(), cls.contiguous()
+        out = ops.stage1_loss_fwd(f, g, cls, k, w)
+        ctx.save_for_backward(f, g, cls)
+        ctx.k, ctx.w = k, w
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, d0, d1, d4, d5):
+        f, g, cls = ctx.saved_tensors
+        dout = torch.zeros(4, device=f.device, dtype=f32)
+        for i, d in enumerate((d0, d1, d4, d5)):
+            if d is not None:
+                dout[i].copy_(d)
+        df, dcls = ops.stage1_loss_bwd(f, g, cls, dout, ctx.k, ctx.w)
+        return df, None, dcls, None, None
+
+
+def stage1_loss(f, g, cls, k, w):
+    return _LossFn.apply(f, g, cls, k, w)
 
 
 class ClipEngine(_EngineBase):
@@ -94,12 +139,15 @@ class ClipEngine(_EngineBase):
         if not self.module.is_vit:
             self.resnet.refresh()
 
+    def encode_patches(self, patches, n):
+        """bf16 patches [n*49, 3072] -> bf16 features [n, 512] (autograd edge to the patches: dgrad-only backward)."""
+        self.ensure_fresh()
+        return _VitFn.apply(patches, self, n)
+
     def encode_image(self, image):
         self.ensure_fresh()
         if self.module.is_vit:
-            n = image.shape[0]
-            patches = patchify(image)
-            return _VitFn.apply(patches, self, n).float()
+            return self.encode_patches(patchify(image), image.shape[0]).float()
         with torch.no_grad():
             c4, _ = self.resnet.forward(image.float(), train=False)
         return c4.permute(0, 3, 1, 2).float()

@@ -200,7 +200,7 @@ def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
 
 # --------------------------------------------------------------------------------------- generic / batched entry
 def gemm_ex(a, b, out, M, N, K, a_mode=L.OP_K2D, b_mode=L.OP_K2D, lda=None, ldb=None, ldd=None, batch=1, a_bs=0, b_bs=0,
-            d_bs=0, bias=None, act=L.ACT_NONE, atomic=0, split_k=1, block_n=None):
+            d_bs=0, bias=None, act=L.ACT_NONE, atomic=0, split_k=1, block_n=None, scale=0.0, residual=None):
     """out[b] (M x N, row stride ldd) = act(A[b] . B[b]^T-ish + bias) on explicit extents / strides, so strided views
     (e.g. the Q/K/V thirds of a fused projection) and per-image batches can be used without copies.
     a_mode K2D: A[b] is [M, K] rows (stride lda);  MN2D: A[b] is [K, M] rows.   b likewise with N."""
@@ -215,6 +215,7 @@ def gemm_ex(a, b, out, M, N, K, a_mode=L.OP_K2D, b_mode=L.OP_K2D, lda=None, ldb=
         bn = min(bn, 128)
     d = _desc(a=L.ptr(a), b=L.ptr(b), d=L.ptr(out), bias=L.ptr(bias), a_mode=a_mode, b_mode=b_mode, M=M, N=N, K=K, lda=lda,
               ldb=ldb, ldd=ldd, taps=1, block_n=bn, split_k=split_k, act=act, out_dtype=L.DT_F32 if f32 else L.DT_BF16,
-              atomic=atomic, batch=batch, a_batch_stride=a_bs, b_batch_stride=b_bs, d_batch_stride=d_bs)
+              atomic=atomic, batch=batch, a_batch_stride=a_bs, b_batch_stride=b_bs, d_batch_stride=d_bs, scale=scale,
+              residual=L.ptr(residual))
     L.gemm_raw(d)
     return out

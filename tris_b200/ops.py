@@ -171,6 +171,23 @@ def l2norm_fwd(x):
     return y, inv
 
 
+def l2norm_fwd_f32(x, want_f32=True):
+    """fp32 rows in -> (y bf16, y fp32 | None, inv_norm)."""
+    y = torch.empty(x.shape, device=x.device, dtype=bf16)
+    y32 = torch.empty_like(x) if want_f32 else None
+    inv = torch.empty((x.shape[0],), device=x.device, dtype=f32)
+    L.call("tris_l2norm_fwd_f32", _vp(x), _vp(y), _vp(y32), _vp(inv), x.shape[0], x.shape[1])
+    return y, y32, inv
+
+
+def center_pixels(x32, batch):
+    """x fp32 [B*P, C] -> bf16 x - mean_pixels(x) per (image, channel)."""
+    rows, c = x32.shape
+    out = torch.empty((rows, c), device=x32.device, dtype=bf16)
+    L.call("tris_center_pixels", _vp(x32), _vp(out), batch, rows // batch, c)
+    return out
+
+
 def l2norm_bwd(dy, y, inv):
     dx = torch.empty_like(y)
     L.call("tris_l2norm_bwd", _vp(dy), _vp(y), _vp(inv), _vp(dx), y.shape[0], y.shape[1])
@@ -200,3 +217,113 @@ def axpby(x, y, a, b):
     """y = a*x + b*y (bf16, in place on y)."""
     L.call("tris_axpby", _vp(x), _vp(y), C.c_float(a), C.c_float(b), C.c_long(x.numel()))
     return y
+
+
+# ------------------------------------------------------------------ Stage-1 head (head.cu)
+def xattn_softmax_fwd(S1, S2T, T, scale):
+    B, Pn, Tp = S1.shape
+    PA = torch.empty((B, Pn, Tp), device=S1.device, dtype=bf16)
+    PAc, PTt = torch.empty_like(PA), torch.empty_like(PA)
+    L.call("tris_xattn_softmax_fwd", _vp(S1), _vp(S2T), _vp(PA), _vp(PAc), _vp(PTt), B, Pn, T, Tp, C.c_float(scale))
+    return PA, PAc, PTt
+
+
+def xattn_softmax_bwd(PA, dPA, PTt, dPTt, T, scale):
+    B, Pn, Tp = PA.shape
+    dS1, dS2T = torch.empty_like(PA), torch.empty_like(PA)
+    L.call("tris_xattn_softmax_bwd", _vp(PA), _vp(dPA), _vp(PTt), _vp(dPTt), _vp(dS1), _vp(dS2T), B, Pn, T, Tp, C.c_float(scale))
+    return dS1, dS2T
+
+
+def bcast_mix(base, x, a):
+    """out[b] = base + a * x[b]   (bf16; base has the shape of one batch entry)."""
+    out = torch.empty_like(x)
+    L.call("tris_bcast_mix", _vp(base), _vp(x), _vp(out), C.c_long(base.numel()), x.numel() // base.numel(), C.c_float(a))
+    return out
+
+
+def batch_sum(x, per_shape, a=1.0, add=None):
+    """out = a * sum_b x[b] (+ add), bf16."""
+    out = torch.empty(per_shape, device=x.device, dtype=bf16)
+    L.call("tris_batch_sum", _vp(x), _vp(add), _vp(out), C.c_long(out.numel()), x.numel() // out.numel(), C.c_float(a))
+    return out
+
+
+def relu_mask(g, y):
+    dst = torch.empty_like(y)
+    L.call("tris_relu_mask", _vp(g), _vp(y), _vp(dst), C.c_long(y.numel()))
+    return dst
+
+
+def head_fwd(R, logit_scale, T, focal_p, focal_l, train):
+    B, Pn, Tp = R.shape
+    dev = R.device
+    maps = torch.empty((B, Pn), device=dev, dtype=f32)
+    es = torch.empty((), device=dev, dtype=f32)
+    cls = fg = mbar = am = None
+    if train:
+        cls = torch.empty((B, T), device=dev, dtype=f32)
+        fg = torch.empty((B,), device=dev, dtype=f32)
+        mbar = torch.empty((B, T), device=dev, dtype=f32)
+        am = torch.empty((B, T), device=dev, dtype=torch.int32)
+    L.call("tris_head_fwd", _vp(R), _vp(logit_scale), _vp(cls), _vp(fg), _vp(maps), _vp(mbar), _vp(am), _vp(es), B, Pn, T, Tp,
+           C.c_float(focal_p), C.c_float(focal_l), int(train))
+    return cls, fg, maps, mbar, am, es
+
+
+def head_bwd(R, logit_scale, dcls, dfg, dmaps, mbar, am, dlogit_scale, T, focal_p, focal_l):
+    B, Pn, Tp = R.shape
+    D = torch.empty((B, Pn, Tp), device=R.device, dtype=bf16)
+    L.call("tris_head_bwd", _vp(R), _vp(logit_scale), _vp(dcls), _vp(dfg), _vp(dmaps), _vp(mbar), _vp(am), _vp(D), _vp(dlogit_scale),
+           B, Pn, T, Tp, C.c_float(focal_p), C.c_float(focal_l))
+    return D
+
+
+def upsample_fwd(maps, h, w, H, W, want_sig=True):
+    B = maps.shape[0]
+    relu = torch.empty((B, 1, H, W), device=maps.device, dtype=f32)
+    sig = torch.empty((B, 1, H, W), device=maps.device, dtype=f32) if want_sig else None
+    L.call("tris_upsample_fwd", _vp(maps), _vp(relu), _vp(sig), B, h, w, H, W)
+    return relu, sig
+
+
+def upsample_bwd(drelu, dsig, sig, h, w):
+    B, _, H, W = sig.shape
+    dmaps = torch.empty((B, h * w), device=sig.device, dtype=f32)
+    L.call("tris_upsample_bwd", _vp(drelu), _vp(dsig), _vp(sig), _vp(dmaps), B, h, w, H, W)
+    return dmaps
+
+
+def mask_resize_fwd(sig, img, out_size=224, ps=32, want_fg=False):
+    """-> (patches bf16 [B*(O/ps)^2, 3*ps*ps], fg f32 [B,3,O,O] | None).  sig None = plain patchify of img."""
+    B, _, S, S2 = img.shape
+    assert S == S2, "square inputs"
+    g = out_size // ps
+    patches = torch.empty((B * g * g, 3 * ps * ps), device=img.device, dtype=bf16)
+    fg = torch.empty((B, 3, out_size, out_size), device=img.device, dtype=f32) if want_fg else None
+    L.call("tris_mask_resize_fwd", _vp(sig), _vp(img), _vp(patches), _vp(fg), B, S, out_size, ps)
+    return patches, fg
+
+
+def mask_resize_bwd(dpatches, img, out_size=224, ps=32):
+    B, _, S, _ = img.shape
+    dcam = torch.empty((B, out_size, out_size), device=img.device, dtype=f32)
+    dsig = torch.empty((B, 1, S, S), device=img.device, dtype=f32)
+    L.call("tris_mask_resize_bwd", _vp(dpatches), _vp(img), _vp(dcam), _vp(dsig), B, S, out_size, ps, launches=2)
+    return dsig
+
+
+def stage1_loss_fwd(f, g, cls, K, w):
+    B, D = f.shape
+    out = torch.empty((4,), device=f.device, dtype=f32)
+    L.call("tris_stage1_loss_fwd", _vp(f), _vp(g), _vp(cls), _vp(out), B, D, K, C.c_float(w[0]), C.c_float(w[1]), C.c_float(w[2]))
+    return out
+
+
+def stage1_loss_bwd(f, g, cls, dout, K, w):
+    B, D = f.shape
+    df = torch.empty_like(f)
+    dcls = torch.empty_like(cls)
+    L.call("tris_stage1_loss_bwd", _vp(f), _vp(g), _vp(cls), _vp(dout), _vp(df), _vp(dcls), B, D, K, C.c_float(w[0]), C.c_float(w[1]),
+           C.c_float(w[2]))
+    return df, dcls

@@ -102,7 +102,7 @@ class ParamStore:
         self.shadow_valid = True
 
     def zero_grad(self):
-        self.grad[: self.n_train].zero_()
+        self.grad.zero_()
 
     def begin_backward_target(self):
         """Called at the start of a training forward: if the caller dropped .grad (zero_grad(set_to_none=True)) the

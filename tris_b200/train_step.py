@@ -12,7 +12,6 @@ import ctypes as C
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from . import _lib as L
 
@@ -20,35 +19,26 @@ f32 = torch.float32
 
 
 def mask_and_resize(sig_out, img, size=224):
-    """train_stage1.py:327-339 (fg only; the bg branch is dead code in the reference)."""
-    if img.shape[2] != size:
-        cam = F.interpolate(sig_out, (size, size), mode="bilinear", align_corners=True)
-        im = F.interpolate(img, (size, size), mode="bilinear", align_corners=True)
-    else:
-        cam, im = sig_out, img
-    return cam * im
+    """train_stage1.py:327-339 (fg only; the bg branch is dead code in the reference) -> fg fp32 [B,3,size,size]."""
+    from . import ops
+    return ops.mask_resize_fwd(sig_out.contiguous(), img.float().contiguous(), size, 32, want_fg=True)[1]
 
 
 def stage1_losses(model, aux, img, word_ids, neg_word_ids, w1=1.0, w4=5.0, w5=2.0):
-    """-> dict(loss, l1, l4, l5) as device scalars (no host sync)."""
+    """-> dict(loss, l1, l4, l5) as device scalars (no host sync).  Every arithmetic step is a libtris_sm100 kernel:
+    TRIS forward -> mask-and-resize straight into ViT patches -> frozen ViT-B/32 (once) + frozen text tower on the
+    positives and negatives in one batch -> fused loss kernel."""
+    from .engine import masked_patches, stage1_loss
     B = img.shape[0]
     cls, _, _, sig_out, _ = model(img, word_ids)
-    fg = mask_and_resize(sig_out, img)
-    f = aux.encode_image(fg)
-    f = f / f.norm(dim=-1, keepdim=True)
-    ids = word_ids if neg_word_ids is None else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
-    g = aux._engine().encode_text_hidden(ids).float()
-    g = g / g.norm(dim=-1, keepdim=True)
-    cos = (f * g[:B]).sum(-1)
-    l1 = -torch.log(cos.clamp(0.0001, 0.9999)).mean()
-    if neg_word_ids is not None:
-        k = neg_word_ids.shape[1]
-        nscore = torch.einsum("bc,bkc->bk", f, g[B:].reshape(B, k, -1))
-        l5 = (-torch.log(1 - nscore)).mean()
-    else:
-        l5 = torch.zeros((), device=img.device)
-    l4 = F.multilabel_soft_margin_loss(cls, torch.eye(B, device=img.device, dtype=cls.dtype))
-    return {"loss": l1 * w1 + l4 * w4 + l5 * w5, "l1": l1, "l4": l4, "l5": l5}
+    eng = aux._engine()
+    patches = masked_patches(sig_out, img)
+    f = eng.encode_patches(patches, B)
+    k = 0 if neg_word_ids is None else neg_word_ids.shape[1]
+    ids = word_ids if k == 0 else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
+    g = eng.encode_text_hidden(ids)
+    loss, l1, l4, l5 = stage1_loss(f, g, cls, k, (w1, w4, w5))
+    return {"loss": loss, "l1": l1, "l4": l4, "l5": l5}
 
 
 class Stage1Trainer:
