@@ -30,6 +30,12 @@ sys.path.insert(0, ROOT)
 
 GFLOP_PER_SAMPLE = 98.0        # algorithmic fwd+bwd work of the necessary step (SURVEY 8d / BASELINE.md)
 METRIC = "Stage-1 training samples/sec (320x320, len20, bs48)"
+# cross-modal attention (K7) + vis/lan projection (K6), forward, per step of 48: 47.75 + 20.2 GFLOP;
+# compulsory bf16 HBM bytes 41.3 MB (K7) + c4 19.7 MB + W_v 4.2 MB
+WORKLOAD = ("Stage-1 train step (configs[1]): CLIP-RN50 + text tower + cross-modal fusion + aux ViT-B/32 losses, 320x320, "
+            "len 20, 3 negatives")
+K7_GFLOP_PER_STEP_B48 = 47.75 + 20.2
+K7_MBYTES_PER_STEP_B48 = 41.3 + 19.7 + 4.2
 
 
 def peaks():
@@ -124,8 +130,9 @@ def run_reference_arm(a):
     line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": a.gpus, "steps": max(1, a.steps),
             "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "Stage-1 train step, 320x320, len 20, 3 negatives, RN50 + aux ViT-B/32 (CPU, fp32)",
-                       "per_step_batch": batch, "note": "oracle port of the reference step; bounded sample of the bs48 workload"},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": 48, "global_batch": 48 * a.gpus, "parallelism": f"dp{a.gpus}",
+                       "sample": f"each step = batch {batch} of the bs48 workload on the host cores (CPU, fp32, oracle port of "
+                                 "train_stage1.py:320-372: fwd + 3 losses + bwd + AdamW)"},
             "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{max(1, a.steps)} step(s) of batch {batch} (fwd + 3 losses + bwd + AdamW), loss {loss:.4f}"},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -234,6 +241,9 @@ def run_gpu_arm(a):
 
         L.gemm_raw = timed_gemm
         gemm.L.gemm_raw = timed_gemm
+        # queue the whole eager step behind a ~60 ms spin kernel so that every launch is already enqueued when the GPU
+        # reaches it: the per-launch event pairs then measure kernel durations, not Python launch gaps
+        torch.cuda._sleep(int(1.2e8))
         trainer.step(*dev[0])
         torch.cuda.synchronize()
         L.gemm_raw = orig
@@ -243,6 +253,30 @@ def run_gpu_arm(a):
         fl = sum(f for _, _, f in gemm_calls)
         prof = {"launches": len(gemm_calls), "ms": t_ms, "tflops": fl / (t_ms * 1e-3) / 1e12, "gflop": fl / 1e9}
 
+    # ---- cross-modal attention group (K6 tail + K7 + K8: north-star "attn HBM GB/s"): forward of the head on resident
+    # c4 / hidden, one CUDA-event pair per repetition, L2 flushed (256 MB write) between repetitions
+    k7 = None
+    if rank == 0:
+        eng = model.engine()
+        g = torch.Generator(device="cuda").manual_seed(7)
+        c4 = torch.randn(B, 10, 10, 2048, device="cuda", generator=g).abs().to(torch.bfloat16)
+        hid = (torch.randn(B, 1024, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ts = []
+        with torch.no_grad():
+            for i in range(8):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                eng.head._fwd(c4, hid, (320, 320), True, save=False)
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+        t_ms = statistics.median(ts[2:])
+        gflop = K7_GFLOP_PER_STEP_B48 * B / 48.0
+        mbytes = K7_MBYTES_PER_STEP_B48 * B / 48.0
+        k7 = {"what": "vis/lan projection + bilateral cross-modal attention + score + response head, forward, eager launches",
+              "ms": t_ms, "gflop": gflop, "tflops": gflop / t_ms, "compulsory_mb": mbytes, "hbm_gbs": mbytes / t_ms}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -261,8 +295,7 @@ def run_gpu_arm(a):
         "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "Stage-1 train step (configs[1]): CLIP-RN50 + text tower + cross-modal fusion + aux ViT-B/32 "
-                               "losses, 320x320, len 20, 3 negatives", "per_gpu_batch": B, "global_batch": B * world,
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "cuda_graph": use_graph, "l2": "activations per step (>5 GB) exceed the 126 MB L2; "
                    f"{n_pool} rotating input batches", "optimizer": "fused AdamW, 2 lr groups, poly 0.9"},
         "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -275,6 +308,7 @@ def run_gpu_arm(a):
                      "launches_per_step": prof["launches"], "kernel_ms_per_step": prof["ms"], "kernel_gflop_per_step": prof["gflop"],
                      "kernel_share_of_step": prof["ms"] / (ms / a.steps),
                      "step_frac_of_peak": (GFLOP_PER_SAMPLE * 1e9 * sps / world) / (sust * 1e12)},
+        "cross_modal_attention": k7,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -85,6 +85,136 @@ typedef struct tris_gemm_desc {
 
 int tris_gemm(const tris_gemm_desc* desc, tris_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Non-GEMM kernels.  Same conventions as above.  `void*` activation buffers are bf16 unless stated; NHWC for
+ * image-tower activations, [rows, channels] row-major elsewhere; statistics / losses / gradients of parameters fp32.
+ * Each entry names the reference arithmetic it replaces (paths relative to fawnliu/TRIS). */
+
+/* ---- bn_act.cu */
+/* nn.BatchNorm2d (train: batch statistics from the GEMM epilogue sums + running-stat update; eval: running stats) + ReLU
+ * + AvgPool2d(pool) + residual add / second BN branch (downsample) -- CLIP/clip/model.py:18-28,36-40,42-55. */
+int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, const float* beta0, float* rm0,
+    float* rv0, float* save_mean0, float* save_invstd0, const void* y1, const float* stats1, const float* gamma1,
+    const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1, const void* residual, void*
+    out, int n, int h, int w, int c, int pool, int relu, int train, float momentum, float eps, tris_stream_t
+    stream);
+/* backward of the above: per-channel reductions (dgamma, dbeta) then dy (and the residual gradient g_out) -- model.py:42-55. */
+int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* gamma0, const float* beta0, const
+    float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0, const void* y1, const
+    float* gamma1, const float* beta1, const float* save_mean1, const float* save_invstd1, float* dgamma1, float*
+    dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, tris_stream_t stream);
+/* nn.AvgPool2d(2) on NHWC bf16 (the anti-aliased stride of the downsample branch, model.py:37). */
+int tris_avgpool2_fwd(const void* x, void* out, int n, int h, int w, int c, tris_stream_t stream);
+/* its adjoint (+ optional accumulate source). */
+int tris_avgpool2_bwd(const void* dout, const void* add, void* dx, int n, int h, int w, int c, tris_stream_t
+    stream);
+
+/* ---- head.cu */
+/* the two softmaxes of bilateral_prompt (model/attn.py:122 text axis, :125 pixel axis) + pixel-centred copy of the first. */
+int tris_xattn_softmax_fwd(const float* S1, const float* S2T, void* PA, void* PAc, void* PTt, int B, int P, int T,
+    int Tp, float scale, tris_stream_t stream);
+/* softmax backward for both. */
+int tris_xattn_softmax_bwd(const void* PA, const float* dPA, const void* PTt, const float* dPTt, void* dS1, void*
+    dS2T, int B, int P, int T, int Tp, float scale, tris_stream_t stream);
+/* norm_lan + 0.1 * new_lan with norm_lan shared by all images (model/model_stage1.py:66,74). */
+int tris_bcast_mix(const void* base, const void* x, void* out, long per, int B, float a, tris_stream_t stream);
+/* adjoint of the broadcast above (sum over images). */
+int tris_batch_sum(const void* x, const void* add, void* out, long per, int B, float a, tris_stream_t stream);
+/* ReLU backward of the text projections (attn.py:87-97) from an fp32 gradient. */
+int tris_relu_mask(const float* g, const void* y, void* dst, long n, tris_stream_t stream);
+/* response head: bg class, 49-way softmax, mean/max/focal scores, diagonal maps (model/model_stage1.py:80-114, focal_loss :122-123). */
+int tris_head_fwd(const float* R, const float* logit_scale, float* cls_out, float* cls_fg, float* maps, float* mbar,
+    int* argmax, float* es_out, int B, int P, int T, int Tp, float focal_p, float focal_l, int train, tris_stream_t
+    stream);
+/* its backward: dL/d(score/exp(logit_scale)) in bf16 and d logit_scale. */
+int tris_head_bwd(const float* R, const float* logit_scale, const float* dcls_out, const float* dcls_fg, const
+    float* dmaps, const float* mbar, const int* argmax, void* D, float* dlogit_scale, int B, int P, int T, int Tp,
+    float focal_p, float focal_l, tris_stream_t stream);
+/* Upsample(bilinear, align_corners=False) + ReLU / sigmoid (model/utils.py:5-10, model_stage1.py:114-119). */
+int tris_upsample_fwd(const float* maps, float* relu_out, float* sig_out, int B, int h, int w, int H, int W,
+    tris_stream_t stream);
+/* adjoint (gather form) onto the h x w logits. */
+int tris_upsample_bwd(const float* drelu, const float* dsig, const float* sig, float* dmaps, int B, int h, int w,
+    int H, int W, tris_stream_t stream);
+/* fg = bilinear_ac(sig->O) * bilinear_ac(img->O) as ViT patches and/or NCHW fp32 (train_stage1.py:327-339); sig NULL = patchify only. */
+int tris_mask_resize_fwd(const float* sig, const float* img, void* patches, float* fg, int B, int S, int O, int ps,
+    tris_stream_t stream);
+/* gradient of the above w.r.t. the sigmoid map. */
+int tris_mask_resize_bwd(const void* dpatches, const float* img, float* dcam, float* dsig, int B, int S, int O, int
+    ps, tris_stream_t stream);
+/* F.interpolate(mode="bilinear", align_corners=True) of fp32 [nc, H, W] maps to the original image size (validate.py:180, demo.py:94). */
+int tris_resize_bilinear_ac(const float* src, float* dst, long nc, int H, int W, int OH, int OW, tris_stream_t stream);
+/* fg loss (clip_forward + MaxLoss, train_stage1.py:263-284,340), negative loss (:342-353), multilabel soft margin (:354), weighted sum (:364). */
+int tris_stage1_loss_fwd(const void* f, const void* g, const float* cls, float* out, int B, int D, int K, float w1,
+    float w4, float w5, tris_stream_t stream);
+/* gradients of the weighted sum w.r.t. the image features and cls_out. */
+int tris_stage1_loss_bwd(const void* f, const void* g, const float* cls, const float* dout, void* df, float* dcls,
+    int B, int D, int K, float w1, float w4, float w5, tris_stream_t stream);
+
+/* ---- misc.cu */
+/* data movement of the stride-2 3x3 stem conv on the fp32 NCHW image (model.py:212-217,255-258). */
+int tris_stem_im2col(const float* img, void* col, int n, int h, int w, tris_stream_t stream);
+/* fp32 master -> bf16 operand copy of all parameters. */
+int tris_f32_to_bf16(const float* src, void* dst, long n, tris_stream_t stream);
+/* OIHW fp32 -> [Cout, taps*Cin] bf16 (tap-major K) for the implicit-GEMM convs. */
+int tris_pack_conv(const float* w, void* out, int co, int ci, int khw, int co_pad, int ci_pad, tris_stream_t
+    stream);
+/* inverse layout change for the weight gradient (adds into the OIHW gradient). */
+int tris_unpack_conv_grad(const float* gp, float* gw, int co, int ci, int khw, int ci_pad, tris_stream_t stream);
+/* x / x.norm(dim=-1) (model_stage1.py:68-69), bf16 rows. */
+int tris_l2norm_fwd(const void* x, void* y, float* inv_norm, int rows, int D, tris_stream_t stream);
+/* same from fp32 rows, optionally also emitting fp32 output. */
+int tris_l2norm_fwd_f32(const float* x, void* y, float* y32, float* inv_norm, int rows, int D, tris_stream_t
+    stream);
+/* x - mean over the pixels of each image (exact under the InstanceNorm that follows, attn.py:72-86). */
+int tris_center_pixels(const float* x, void* out, int B, int P, int C, tris_stream_t stream);
+/* backward of the L2 normalisation. */
+int tris_l2norm_bwd(const void* dy, const void* y, const float* inv_norm, void* dx, int rows, int D, tris_stream_t
+    stream);
+/* nn.InstanceNorm2d(affine) [+ ReLU] [+ 0.1-residual mix] (attn.py:72-86,102-105; model_stage1.py:73). */
+int tris_instnorm_fwd(const void* x, const float* gamma, const float* beta, const void* mix_add, void* out, float*
+    mean, float* invstd, int batch, int P, int C, float mix_scale, int relu, float eps, tris_stream_t stream);
+/* its backward (dgamma / dbeta accumulated). */
+int tris_instnorm_bwd(const void* dout, const void* x, const float* gamma, const float* beta, const float* mean,
+    const float* invstd, void* dx, float* dgamma, float* dbeta, int batch, int P, int C, float mix_scale, int relu,
+    tris_stream_t stream);
+/* y = a*x + b*y on bf16. */
+int tris_axpby(const void* x, void* y, float a, float b, long n, tris_stream_t stream);
+
+/* ---- optim.cu */
+/* torch.optim.AdamW over the flat buffer, two lr groups, poly-0.9 LambdaLR, 1/world gradient scaling, bf16 shadow refresh
+ * (train_stage1.py:133-144,368-372). */
+int tris_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long n, long n_group0, int* step,
+    float max_iter, float lr0, float lr1, float beta1, float beta2, float eps, float wd, float grad_scale, float
+    power, tris_stream_t stream);
+
+/* ---- transformer.cu */
+/* token_embedding[ids] + positional_embedding, EOT index = argmax(ids) (model.py:552-564). */
+int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D,
+    tris_stream_t stream);
+/* scatter-add into the embedding / positional gradients. */
+int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, int L, int D, tris_stream_t stream);
+/* LayerNorm in fp32 (model.py:352-358). */
+int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int
+    rows, int D, float eps, tris_stream_t stream);
+/* its backward (+ residual-gradient add, dgamma / dbeta). */
+int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+    const void* add, void* dx, float* dgamma, float* dbeta, int rows, int D, tris_stream_t stream);
+/* softmax(q k^T / 8 [+ causal mask]) v per (sample, head), head dim 64 (nn.MultiheadAttention in model.py:366-386). */
+int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causal, tris_stream_t stream);
+/* its backward (dq, dk, dv packed like qkv). */
+int tris_attn_bwd(const void* qkv, const void* dout, void* dqkv, int n, int L, int heads, int causal, tris_stream_t
+    stream);
+/* row gather (EOT / class-token pooling, model.py:562, :445). */
+int tris_gather_rows(const void* x, const int* idx, void* out, int rows, int D, tris_stream_t stream);
+/* adjoint of the gather into a zero tensor. */
+int tris_scatter_rows(const void* src, const int* idx, void* out, int rows, int D, tris_stream_t stream);
+/* out[c] += sum_r x[r,c] (bias gradients). */
+int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream);
+/* class token + patch tokens + positional embedding (model.py:436-441). */
+int tris_vit_assemble(const void* patch, const float* cls, const float* pos, void* tok, int n, int T, int D,
+    tris_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -233,3 +233,32 @@ def test_head_eval_single_sentence(tris):
     (out,) = eng.head.forward(c4, hidden, (320, 320), False)
     assert out.shape == (1, 1, 320, 320)
     assert rel(out, ref) < 2e-2
+
+
+def test_resize_bilinear_ac(K):
+    x = rnd(2, 1, 320, 320, seed=30)
+    got = K.resize_bilinear_ac(x, 480, 640)
+    ref = F.interpolate(x, (480, 640), mode="bilinear", align_corners=True)
+    assert rel(got, ref) < 2e-4
+
+
+def test_inference_drivers_synthetic(tris):
+    """validate / validate_same_sentence (PRMS) / cached-feature path agree with the plain eval forward."""
+    import validate as V
+    from tris_b200 import clip_model
+    m, eng, sd = tris
+    args = _args()
+    args.size, args.val_refs, args.save_cam, args.cam_save_dir, args.name_save_dir, args.dataset = 320, 3, False, None, None, "refcoco"
+    m.eval()
+    idx, img, word_ids, target = next(V.synthetic_refs(args, 1))
+    with torch.no_grad():
+        full = m(img.cuda(), word_ids[:, :, 0].cuda().contiguous())
+        c4 = m.image_features(img.cuda())
+        cached = m.respond(c4, word_ids[:, :, 0].cuda().contiguous(), (320, 320))
+    assert torch.equal(full, cached)
+    miou, hit = V.validate(args, V.synthetic_refs(args, 3), m)
+    assert 0.0 <= miou <= 1.0 and 0.0 <= hit <= 1.0
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+    miou2 = V.validate_same_sentence(args, V.synthetic_refs(args, 3), m, aux)
+    assert 0.0 <= miou2 <= 1.0
+    m.train()

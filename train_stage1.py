@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Stage-1 training entry point (counterpart of the reference's train_stage1.py:44-260,286-411,415-447).
+
+    python train_stage1.py --synthetic --batch_size 48 --size 320 --max_query_len 20 --negative_samples 3 --epoch 1
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 train_stage1.py --synthetic --distributed ...
+
+Same recipe as scripts/train_stage1.sh:3-16: AdamW (backbone lr*lr_multi, new modules lr, wd), poly-0.9 LR per step,
+losses w1*fg + w4*cls + w5*neg with a frozen CLIP ViT-B/32, validation + checkpoint per epoch (state_dict layout of
+utils/util.py:50-77: {"model", "epoch"} with the reference's 518 keys).  RefCOCO loading (dataset/ReferDataset.py) is
+out of scope offline: without --synthetic the script stops with an explanation.
+"""
+import os
+import sys
+import time
+import warnings
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from args import get_parser  # noqa: E402
+
+
+def main(args):
+    warnings.simplefilter("ignore")
+    from tris_b200 import clip_model as clip
+    from tris_b200 import dp
+    from tris_b200.model_stage1 import TRIS
+    from tris_b200.synthetic import synthetic_batch
+    from tris_b200.train_step import Stage1Trainer
+    import validate as V
+    rank, local, world = dp.env_rank()
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not args.synthetic:
+        raise SystemExit("train_stage1.py: RefCOCO loaders are out of scope of this build (no dataset offline); use --synthetic")
+    torch.manual_seed(1234)
+    model = TRIS(args).cuda().train()
+    if args.pretrain:
+        ck = torch.load(args.pretrain, map_location="cpu")
+        print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
+    aux, _ = clip.load("ViT-B-32", device="cuda", jit=False, txt_length=args.max_query_len)
+    max_iter = args.steps_per_epoch * args.epoch
+    trainer = Stage1Trainer(model, aux, max_iter=max_iter, lr=args.lr, lr_multi=args.lr_multi, weight_decay=args.weight_decay,
+                            w=(args.w1, args.w4, args.w5))
+    B, k = args.batch_size, args.negative_samples
+    batch = lambda i: tuple(None if t is None else t.cuda(non_blocking=True)
+                            for t in synthetic_batch(B, args.size, args.max_query_len, k, seed=dp.shard_seed(1234, rank, i), pin=True))
+    if not args.no_graph:
+        trainer.capture(*batch(0), warmup=1)
+    best = -1.0
+    for epoch in range(args.start_epoch, args.epoch):
+        t0, seen = time.time(), 0
+        for it in range(args.steps_per_epoch):
+            losses = trainer.step(*batch(epoch * args.steps_per_epoch + it))
+            seen += B * world
+            if rank == 0 and (it + 1) % args.print_freq == 0 or it + 1 == args.steps_per_epoch:
+                vals = {k_: float(v) for k_, v in losses.items()}        # one host sync per print, not per step
+                dt = time.time() - t0
+                if rank == 0:
+                    print(f"epoch {epoch} it {it + 1}/{args.steps_per_epoch} loss {vals['loss']:.4f} l1 {vals['l1']:.4f} "
+                          f"l4 {vals['l4']:.4f} l5 {vals['l5']:.4f}  {seen / dt:.0f} samples/s "
+                          f"mem {torch.cuda.max_memory_allocated() / 2**20:.0f} MB", flush=True)
+        miou, hit = V.validate(args, V.synthetic_refs(args, args.val_refs, rank, world), model, rank)
+        if rank == 0:
+            print(f"epoch {epoch} val mIoU {miou:.4f} hit {hit:.4f}")
+            if args.output and miou > best:
+                best = miou
+                os.makedirs(args.output, exist_ok=True)
+                torch.save({"model": model.state_dict(), "epoch": epoch}, os.path.join(args.output, f"stage1_best_{epoch}.pth"))
+        model.train()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(get_parser().parse_args())

@@ -63,7 +63,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         for _, log in res:
             sys.stderr.write(log)
     objs = [o for o, _ in res]
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     open(stamp, "w").write(dg)

@@ -162,9 +162,18 @@ struct BwdParams {
     float count;
 };
 
-// g at input position (irow) for channel group c0, already masked and pool-scaled.
-__device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long irow, long orow, int c0, const Vec8& y0,
-                                            const float (&sc0)[8], const float (&sh0)[8]) {
+// Per-channel constants live in shared memory (loaded per use as two LDS.128) instead of ~90 registers, which kept the
+// old kernels at 2 CTAs/SM (128 registers/thread, 23 % of the warps) and latency-bound at ~45 % of the HBM rate.
+__device__ __forceinline__ Vec8 lds8(const float* s) {
+    Vec8 o;
+    const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+    o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+    return o;
+}
+
+// g at output row orow for channel group c0, masked (ReLU) and pool-scaled.  sc/sh: smem scale/shift of branch 0 (mask
+// recompute when the forward output was not kept).
+__device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long orow, int c0, const Vec8& y0, const float* s_sc, const float* s_sh) {
     Vec8 g = ld8(p.dout + orow * p.c + c0);
     if (p.pool == 2) {
 #pragma unroll
@@ -176,8 +185,9 @@ __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long irow, long 
 #pragma unroll
             for (int i = 0; i < 8; ++i) g.v[i] = o.v[i] > 0.f ? g.v[i] : 0.f;
         } else {
+            const Vec8 sc = lds8(s_sc + c0), sh = lds8(s_sh + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g.v[i] = fmaf(y0.v[i], sc0[i], sh0[i]) > 0.f ? g.v[i] : 0.f;
+            for (int i = 0; i < 8; ++i) g.v[i] = fmaf(y0.v[i], sc.v[i], sh.v[i]) > 0.f ? g.v[i] : 0.f;
         }
     }
     return g;
@@ -192,46 +202,52 @@ __device__ __forceinline__ long out_row_of(const BwdParams& p, long irow) {
     return (ni * (p.h / 2) + (y >> 1)) * (p.w / 2) + (x >> 1);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdParams p) {
+// dbeta = sum g ; dgamma = invstd * sum g (y - mean).   smem: sc0 [C], sh0 [C], mu0 [C], mu1 [C], then the reduction scratch.
+template <bool DUAL>
+__global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdParams p) {
     extern __shared__ float sm[];
-    float* red = sm;   // [kThreads * 8] scratch reused per quantity
-    const bool dual = p.b1.y != nullptr;
+    float* s_sc = sm;
+    float* s_sh = sm + p.c;
+    float* s_mu0 = sm + 2 * p.c;
+    float* s_mu1 = sm + 3 * p.c;
+    float* red = sm + 4 * p.c;   // [kThreads * 8]
+    for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
+        const float invstd = p.b0.save_invstd[c], mean = p.b0.save_mean[c];
+        const float sc = p.b0.gamma[c] * invstd;
+        s_sc[c] = sc; s_sh[c] = p.b0.beta[c] - mean * sc; s_mu0[c] = mean;
+        s_mu1[c] = DUAL ? p.b1.save_mean[c] : 0.f;
+    }
+    __syncthreads();
     const int vecs = p.c >> 3;
     const long rows = static_cast<long>(p.n) * p.h * p.w;
     // grid stride is a multiple of `vecs` (vecs | kThreads), so each thread keeps one channel group.
     const long start = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x;
     const int c0 = static_cast<int>(start % vecs) * 8;
     const long row_step = static_cast<long>(gridDim.x) * kThreads / vecs;
-    float sc0[8], sh0[8], mu0[8], is0[8], mu1[8], is1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float invstd = p.b0.save_invstd[c0 + i], mean = p.b0.save_mean[c0 + i];
-        const float sc = p.b0.gamma[c0 + i] * invstd;
-        sc0[i] = sc; sh0[i] = p.b0.beta[c0 + i] - mean * sc; mu0[i] = mean; is0[i] = invstd;
-        mu1[i] = dual ? p.b1.save_mean[c0 + i] : 0.f;
-        is1[i] = dual ? p.b1.save_invstd[c0 + i] : 0.f;
-    }
     float dg0[8], db[8], dg1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dg0[i] = db[i] = dg1[i] = 0.f;
     for (long irow = start / vecs; irow < rows; irow += row_step) {
         const long orow = out_row_of(p, irow);
-        Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
-        Vec8 g = masked_grad(p, irow, orow, c0, y0, sc0, sh0);
+        const Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
+        Vec8 y1;
+        if (DUAL) y1 = ld8(p.b1.y + irow * p.c + c0);
+        const Vec8 g = masked_grad(p, orow, c0, y0, s_sc, s_sh);
+        const Vec8 mu0 = lds8(s_mu0 + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             db[i] += g.v[i];
-            dg0[i] = fmaf(g.v[i], (y0.v[i] - mu0[i]) * is0[i], dg0[i]);
+            dg0[i] = fmaf(g.v[i], y0.v[i] - mu0.v[i], dg0[i]);
         }
-        if (dual) {
-            Vec8 y1 = ld8(p.b1.y + irow * p.c + c0);
+        if (DUAL) {
+            const Vec8 mu1 = lds8(s_mu1 + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dg1[i] = fmaf(g.v[i], (y1.v[i] - mu1[i]) * is1[i], dg1[i]);
+            for (int i = 0; i < 8; ++i) dg1[i] = fmaf(g.v[i], y1.v[i] - mu1.v[i], dg1[i]);
         }
     }
     // block reduction over the kThreads/vecs threads that share a channel group
     const int per = kThreads / vecs;   // threads per channel group (>= 1)
-    auto block_sum = [&](float (&x)[8], float* dst) {
+    auto block_sum = [&](float (&x)[8], float* dst, const float* scale) {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = x[i];
@@ -240,61 +256,66 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdParams
             const int g = c >> 3, i = c & 7;
             float s = 0.f;
             for (int k = 0; k < per; ++k) s += red[(g + k * vecs) * 8 + i];
-            atomicAdd(dst + c, s);
+            atomicAdd(dst + c, scale != nullptr ? s * scale[c] : s);
         }
     };
-    block_sum(db, p.dbeta0);
-    block_sum(dg0, p.dgamma0);
-    if (dual) {
-        block_sum(db, p.dbeta1);
-        block_sum(dg1, p.dgamma1);
+    block_sum(db, p.dbeta0, nullptr);
+    block_sum(dg0, p.dgamma0, p.b0.save_invstd);
+    if (DUAL) {
+        block_sum(db, p.dbeta1, nullptr);
+        block_sum(dg1, p.dgamma1, p.b1.save_invstd);
     }
 }
 
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const BwdParams p) {
-    const bool dual = p.b1.y != nullptr;
+// dy = a g + b y + c per channel with  a = gamma*invstd,  b = -a*invstd*dgamma/N,  c = a*(invstd*dgamma/N*mean - dbeta/N).
+// smem: sc0, sh0, b0, c0, (dual) a1, b1, c1  -- each [C].
+template <bool DUAL>
+__global__ void __launch_bounds__(kThreads, 4) bn_bwd_apply_kernel(const BwdParams p) {
+    extern __shared__ float sm[];
+    float* s_sc = sm;
+    float* s_sh = sm + p.c;
+    float* s_b0 = sm + 2 * p.c;
+    float* s_c0 = sm + 3 * p.c;
+    float* s_a1 = sm + 4 * p.c;
+    float* s_b1 = sm + 5 * p.c;
+    float* s_c1 = sm + 6 * p.c;
+    const float inv_count = 1.f / p.count;
+    for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
+        const float invstd = p.b0.save_invstd[c], mean = p.b0.save_mean[c];
+        const float sc = p.b0.gamma[c] * invstd;
+        const float k = p.dgamma0[c] * inv_count * invstd, m = p.dbeta0[c] * inv_count;
+        s_sc[c] = sc; s_sh[c] = p.b0.beta[c] - mean * sc;
+        s_b0[c] = -sc * k; s_c0[c] = sc * (k * mean - m);
+        if (DUAL) {
+            const float is1 = p.b1.save_invstd[c], mu1 = p.b1.save_mean[c];
+            const float a1 = p.b1.gamma[c] * is1;
+            const float k1 = p.dgamma1[c] * inv_count * is1, m1 = p.dbeta1[c] * inv_count;
+            s_a1[c] = a1; s_b1[c] = -a1 * k1; s_c1[c] = a1 * (k1 * mu1 - m1);
+        }
+    }
+    __syncthreads();
     const int vecs = p.c >> 3;
     const long rows = static_cast<long>(p.n) * p.h * p.w;
     const long start = static_cast<long>(blockIdx.x) * kThreads + threadIdx.x;
     const int c0 = static_cast<int>(start % vecs) * 8;
     const long row_step = static_cast<long>(gridDim.x) * kThreads / vecs;
-    float sc0[8], sh0[8], mu0[8], is0[8], k0[8], m0[8], mu1[8], is1[8], a1[8], k1[8], m1[8];
-    const float inv_count = 1.f / p.count;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float invstd = p.b0.save_invstd[c0 + i], mean = p.b0.save_mean[c0 + i];
-        const float sc = p.b0.gamma[c0 + i] * invstd;
-        sc0[i] = sc; sh0[i] = p.b0.beta[c0 + i] - mean * sc; mu0[i] = mean; is0[i] = invstd;
-        k0[i] = p.dgamma0[c0 + i] * inv_count;
-        m0[i] = p.dbeta0[c0 + i] * inv_count;
-        if (dual) {
-            mu1[i] = p.b1.save_mean[c0 + i];
-            is1[i] = p.b1.save_invstd[c0 + i];
-            a1[i] = p.b1.gamma[c0 + i] * is1[i];
-            k1[i] = p.dgamma1[c0 + i] * inv_count;
-            m1[i] = p.dbeta1[c0 + i] * inv_count;
-        } else {
-            mu1[i] = is1[i] = a1[i] = k1[i] = m1[i] = 0.f;
-        }
-    }
     for (long irow = start / vecs; irow < rows; irow += row_step) {
         const long orow = out_row_of(p, irow);
-        Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
-        Vec8 g = masked_grad(p, irow, orow, c0, y0, sc0, sh0);
+        const Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
+        Vec8 y1;
+        if (DUAL) y1 = ld8(p.b1.y + irow * p.c + c0);
+        const Vec8 g = masked_grad(p, orow, c0, y0, s_sc, s_sh);
         Vec8 d;
+        {
+            const Vec8 a = lds8(s_sc + c0), b = lds8(s_b0 + c0), c = lds8(s_c0 + c0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xhat = (y0.v[i] - mu0[i]) * is0[i];
-            d.v[i] = sc0[i] * (g.v[i] - m0[i] - xhat * k0[i]);
+            for (int i = 0; i < 8; ++i) d.v[i] = fmaf(a.v[i], g.v[i], fmaf(b.v[i], y0.v[i], c.v[i]));
         }
         st8(p.dy0 + irow * p.c + c0, d);
-        if (dual) {
-            Vec8 y1 = ld8(p.b1.y + irow * p.c + c0);
+        if (DUAL) {
+            const Vec8 a = lds8(s_a1 + c0), b = lds8(s_b1 + c0), c = lds8(s_c1 + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xhat = (y1.v[i] - mu1[i]) * is1[i];
-                d.v[i] = a1[i] * (g.v[i] - m1[i] - xhat * k1[i]);
-            }
+            for (int i = 0; i < 8; ++i) d.v[i] = fmaf(a.v[i], g.v[i], fmaf(b.v[i], y1.v[i], c.v[i]));
             st8(p.dy1 + irow * p.c + c0, d);
         }
         if (p.g_out != nullptr) st8(p.g_out + irow * p.c + c0, g);
@@ -416,9 +437,18 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     // cap the reduction grid: each block ends with 2-4 * C atomics
     int rgrid = grid_for(total);
     if (rgrid > 2 * tris::sm_count()) rgrid = 2 * tris::sm_count();
-    bn_bwd_reduce_kernel<<<rgrid, kThreads, kThreads * 8 * sizeof(float), s>>>(p);
+    const size_t rsmem = (4 * c + kThreads * 8) * sizeof(float), asmem = 7 * c * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
+        attr = true;
+    }
+    if (y1 != nullptr) bn_bwd_reduce_kernel<true><<<rgrid, kThreads, rsmem, s>>>(p);
+    else bn_bwd_reduce_kernel<false><<<rgrid, kThreads, rsmem, s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
-    bn_bwd_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+    if (y1 != nullptr) bn_bwd_apply_kernel<true><<<grid_for(total), kThreads, asmem, s>>>(p);
+    else bn_bwd_apply_kernel<false><<<grid_for(total), kThreads, asmem, s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_apply_kernel");
     return TRIS_OK;
 }

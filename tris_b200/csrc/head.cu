@@ -484,6 +484,24 @@ __global__ void __launch_bounds__(256) mask_resize_dsig_kernel(const float* __re
     }
 }
 
+// plain bilinear resize, align_corners=True: src f32 [NC, H, W] -> dst f32 [NC, OH, OW]  (validate.py:180, demo.py:94)
+__global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict__ src, float* __restrict__ dst, long NC, int H, int W,
+                                                        int OH, int OW) {
+    const long total = NC * OH * OW;
+    const float sy = OH > 1 ? static_cast<float>(H - 1) / (OH - 1) : 0.f, sx = OW > 1 ? static_cast<float>(W - 1) / (OW - 1) : 0.f;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % OW);
+        const long r = i / OW;
+        const int y = static_cast<int>(r % OH);
+        const long nc = r / OH;
+        int y0, y1, x0, x1;
+        float wy, wx;
+        src_index(y, sy, H, true, y0, y1, wy);
+        src_index(x, sx, W, true, x0, x1, wx);
+        dst[i] = bilerp(src + nc * H * W, W, y0, y1, wy, x0, x1, wx);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ losses (K12)
 // f bf16 [B, D] image features, g bf16 [B*(1+K), D] text features (positives first, then negatives b-major),
 // cls f32 [B, B].   out[4] = {loss, l1, l4, l5}.   Single CTA, warp per sample: deterministic.
@@ -700,6 +718,12 @@ int tris_mask_resize_bwd(const void* dpatches, const float* img, float* dcam, fl
     TRIS_LAUNCH_OK("mask_resize_dcam");
     mask_resize_dsig_kernel<<<grid_for(static_cast<long>(B) * S * S, 256), 256, 0, (cudaStream_t)stream>>>(dcam, dsig, B, S, O);
     TRIS_LAUNCH_OK("mask_resize_dsig");
+    return TRIS_OK;
+}
+
+int tris_resize_bilinear_ac(const float* src, float* dst, long nc, int H, int W, int OH, int OW, tris_stream_t stream) {
+    resize_ac_kernel<<<grid_for(nc * OH * OW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, nc, H, W, OH, OW);
+    TRIS_LAUNCH_OK("resize_bilinear_ac");
     return TRIS_OK;
 }
 

@@ -6,6 +6,8 @@ as ``param.grad``); autograd only carries activation gradients between towers.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -17,7 +19,17 @@ from .transformer import TextTower, VitTower
 bf16, f32 = torch.bfloat16, torch.float32
 
 
+OVERLAP = os.environ.get("TRIS_OVERLAP", "1") != "0"   # side-stream overlap of the small text towers with the image tower
+
+
 class _EngineBase:
+    _side = None
+
+    def side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
+
     def __init__(self, module, device, group_of, adjacent=()):
         L.require_device()
         self.module = module
@@ -72,9 +84,23 @@ class _VitFn(torch.autograd.Function):
         return ctx.eng.vit.backward(ctx.rec, dfeat.contiguous()), None, None
 
 
+class _PatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, ps):
+        ctx.shape, ctx.ps = img.shape, ps
+        return ops.mask_resize_fwd(None, img.float().contiguous(), out_size=img.shape[2], ps=ps)[0]
+
+    @staticmethod
+    def backward(ctx, dp):
+        n, c, s, _ = ctx.shape
+        g, ps = s // ctx.ps, ctx.ps
+        return dp.float().view(n, g, g, c, ps, ps).permute(0, 3, 1, 4, 2, 5).reshape(n, c, s, s), None   # layout only
+
+
 def patchify(img, ps=32):
-    """[N,3,S,S] fp32 -> bf16 [N*(S/ps)^2, 3*ps*ps] with k = c*ps*ps + py*ps + px (conv1.weight.reshape(W,-1) order)."""
-    return ops.mask_resize_fwd(None, img.float().contiguous(), out_size=img.shape[2], ps=ps)[0]
+    """[N,3,S,S] fp32 -> bf16 [N*(S/ps)^2, 3*ps*ps] with k = c*ps*ps + py*ps + px (conv1.weight.reshape(W,-1) order).
+    Differentiable w.r.t. img (the reference's training loop back-propagates through encode_image, train_stage1.py:340)."""
+    return _PatchifyFn.apply(img, ps)
 
 
 class _MaskResizeFn(torch.autograd.Function):
@@ -230,8 +256,20 @@ class Stage1Engine(_EngineBase):
         x = x.float()
         if train and torch.is_grad_enabled():
             self.fwd_id += 1
-            c4 = _ResNetFn.apply(self.anchor, x, self)
-            hidden = _TextFn.apply(self.anchor, word_id, self)
+            if OVERLAP:
+                # the text tower (M = B*L = 960 rows: latency-bound kernels on <= 64 SMs) runs on a side stream next to
+                # the image tower; autograd replays its backward on the same side stream next to the RN50 backward
+                main = torch.cuda.current_stream()
+                side = self.side_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    hidden = _TextFn.apply(self.anchor, word_id, self)
+                c4 = _ResNetFn.apply(self.anchor, x, self)
+                main.wait_stream(side)
+                hidden.record_stream(main)
+            else:
+                c4 = _ResNetFn.apply(self.anchor, x, self)
+                hidden = _TextFn.apply(self.anchor, word_id, self)
         else:
             with torch.no_grad():
                 c4, _ = self.resnet.forward(x, train=train)

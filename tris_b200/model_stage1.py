@@ -69,5 +69,22 @@ class TRIS(nn.Module):
         return out if self.training else out[0]
 
 
+    # ------------------------------------------------------------------ inference helpers (validate.py / demo.py)
+    @torch.no_grad()
+    def image_features(self, x):
+        """RN50 tower once per image (eval BN): -> c4 bf16 NHWC.  validate.py re-runs the whole network for every
+        sentence of the same image (validate.py:173-179); the drivers here cache this instead."""
+        eng = self.engine()
+        eng.ensure_fresh()
+        return eng.resnet.forward(x.float(), train=False)[0]
+
+    @torch.no_grad()
+    def respond(self, c4, word_id, img_size):
+        """Response maps relu(seg) [B,1,H,W] for sentences word_id [B,L] paired with cached image features c4 [B,...]."""
+        eng = self.engine()
+        hidden = eng.text.forward(word_id, save=False)[0]
+        return eng.head.forward(c4, hidden, img_size, False)[0]
+
+
 def focal_loss(x, p=1, c=0.1):
     return torch.pow(1 - x, p) * torch.log(c + x)

@@ -327,3 +327,11 @@ def stage1_loss_bwd(f, g, cls, dout, K, w):
     L.call("tris_stage1_loss_bwd", _vp(f), _vp(g), _vp(cls), _vp(dout), _vp(df), _vp(dcls), B, D, K, C.c_float(w[0]), C.c_float(w[1]),
            C.c_float(w[2]))
     return df, dcls
+
+
+def resize_bilinear_ac(x, oh, ow):
+    """fp32 [N,C,H,W] -> [N,C,oh,ow], bilinear, align_corners=True."""
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, oh, ow), device=x.device, dtype=f32)
+    L.call("tris_resize_bilinear_ac", _vp(x.contiguous()), _vp(out), C.c_long(n * c), h, w, oh, ow)
+    return out

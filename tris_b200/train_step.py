@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import dp
 
 f32 = torch.float32
 
@@ -28,15 +29,26 @@ def stage1_losses(model, aux, img, word_ids, neg_word_ids, w1=1.0, w4=5.0, w5=2.
     """-> dict(loss, l1, l4, l5) as device scalars (no host sync).  Every arithmetic step is a libtris_sm100 kernel:
     TRIS forward -> mask-and-resize straight into ViT patches -> frozen ViT-B/32 (once) + frozen text tower on the
     positives and negatives in one batch -> fused loss kernel."""
-    from .engine import masked_patches, stage1_loss
+    from .engine import OVERLAP, masked_patches, stage1_loss
     B = img.shape[0]
-    cls, _, _, sig_out, _ = model(img, word_ids)
     eng = aux._engine()
-    patches = masked_patches(sig_out, img)
-    f = eng.encode_patches(patches, B)
     k = 0 if neg_word_ids is None else neg_word_ids.shape[1]
     ids = word_ids if k == 0 else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
-    g = eng.encode_text_hidden(ids)
+    if OVERLAP:
+        # the frozen text tower depends on the token ids only: it runs on a side stream under the RN50 forward
+        main, side = torch.cuda.current_stream(), eng.side_stream()
+        eng.ensure_fresh()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            g = eng.encode_text_hidden(ids)
+    else:
+        g = eng.encode_text_hidden(ids)
+    cls, _, _, sig_out, _ = model(img, word_ids)
+    patches = masked_patches(sig_out, img)
+    if OVERLAP:
+        main.wait_stream(side)
+        g.record_stream(main)
+    f = eng.encode_patches(patches, B)
     loss, l1, l4, l5 = stage1_loss(f, g, cls, k, (w1, w4, w5))
     return {"loss": loss, "l1": l1, "l4": l4, "l5": l5}
 
@@ -51,8 +63,9 @@ class Stage1Trainer:
         self.v = torch.zeros(st.n_train, device=st.device, dtype=f32)
         self.step_count = torch.zeros(1, device=st.device, dtype=torch.int32)
         self.max_iter, self.lr, self.lr_multi, self.wd = float(max_iter), lr, lr_multi, weight_decay
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dp.world_size(process_group)
         self.pg = process_group
+        dp.broadcast_parameters(st.flat, process_group)      # every rank starts from rank 0's weights (DDP semantics)
         self.graph = None
         self.static = None
         st.publish_grads()            # param.grad = views of the flat buffer; the trainer zeroes the buffer itself
@@ -61,8 +74,7 @@ class Stage1Trainer:
 
     def optimizer_step(self):
         st = self.eng.store
-        if self.world > 1:
-            dist.all_reduce(st.grad[: st.n_train], group=self.pg)
+        dp.all_reduce_gradients(st.grad[: st.n_train], self.pg)   # ONE collective per step (NCCL over NVLink)
         L.call("tris_adamw_step", C.c_void_p(st.flat.data_ptr()), C.c_void_p(st.grad.data_ptr()), C.c_void_p(self.m.data_ptr()),
                C.c_void_p(self.v.data_ptr()), C.c_void_p(st.shadow.data_ptr()), C.c_long(st.n_train),
                C.c_long(st.group_bounds[1]), C.c_void_p(self.step_count.data_ptr()), C.c_float(self.max_iter),

@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Stage-1 evaluation entry point (counterpart of the reference's validate.py:27-103,131-249,253-387).
+
+    python validate.py --synthetic --size 320 --max_query_len 20 --val_refs 5000 [--prms --save_cam --cam_save_dir out/]
+
+`validate`: per ref and sentence, response map -> bilinear(align_corners=True) to the original size -> /max ->
+threshold 1e-9 -> IoU / pointing-game hit (validate.py:179-191).  `validate_same_sentence` (--prms): for every sentence j
+of a ref build fg_j = cam_j * img at 224 and score it against ALL sentences of the ref with the frozen ViT-B/32; keep
+the map with the highest summed score and dump it as `{idx}_{img_id}.npy` (validate.py:304-332,354-359).
+Differences (zero numerical change): the RN50 tower runs once per ref (not once per sentence) and
+each fg / sentence is encoded once (S ViT + S text passes instead of S^2 of each).  Box metrics (OpenCV contours,
+utils/box_eval_utils.py) and dataset loading are out of scope; refs are synthetic.  Refs are sharded round-robin over
+ranks with no communication ("replicas only").
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from args import get_parser  # noqa: E402
+
+
+def synthetic_refs(args, n, rank=0, world=1, sentences=2, orig=(480, 640)):
+    """Generator of (idx, img[1,3,S,S], word_ids[1,L,S_], target[1,oH,oW] int64) like the eval-mode ReferDataset."""
+    from tris_b200 import dp
+    from tris_b200.synthetic import synthetic_batch
+    for idx in dp.shard_range(n, rank, world):
+        img, _, _ = synthetic_batch(1, args.size, args.max_query_len, 0, seed=77000 + idx)
+        _, ids, _ = synthetic_batch(sentences, 32, args.max_query_len, 0, seed=99000 + idx)
+        g = torch.Generator().manual_seed(idx)
+        target = torch.zeros((1, *orig), dtype=torch.int64)
+        y0, x0 = int(torch.randint(0, orig[0] // 2, (1,), generator=g)), int(torch.randint(0, orig[1] // 2, (1,), generator=g))
+        target[:, y0:y0 + orig[0] // 3, x0:x0 + orig[1] // 3] = 1
+        yield idx, img, ids.t().unsqueeze(0).contiguous(), target
+
+
+def _to_original(cam, size):
+    from tris_b200 import ops
+    return ops.resize_bilinear_ac(cam.contiguous(), size[0], size[1])
+
+
+def _iou_hit(cam, target):
+    cam = cam / (cam.max() + 1e-5)
+    pred = cam > 1e-9
+    tgt = target.bool()
+    inter, union = (pred & tgt).sum().item(), (pred | tgt).sum().item()
+    peak = int(cam.reshape(-1).argmax())
+    hit = bool(tgt.reshape(-1)[peak])
+    return inter / max(union, 1), hit, cam
+
+
+@torch.no_grad()
+def validate(args, refs, model, local_rank=0):
+    model.eval()
+    ious, hits = [], []
+    for idx, img, word_ids, target in refs:
+        img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
+        c4 = model.image_features(img)                          # once per ref
+        for j in range(word_ids.shape[-1]):
+            out = model.respond(c4, word_ids[:, :, j].contiguous(), img.shape[2:])
+            cam = _to_original(out, target.shape[-2:])[0, 0]
+            iou, hit, cam = _iou_hit(cam, target[0])
+            ious.append(iou)
+            hits.append(hit)
+            if args.save_cam and args.cam_save_dir:
+                os.makedirs(args.cam_save_dir, exist_ok=True)
+                np.save(os.path.join(args.cam_save_dir, f"{idx}_{j}.npy"), cam.cpu().numpy())
+    return float(np.mean(ious)) if ious else 0.0, float(np.mean(hits)) if hits else 0.0
+
+
+@torch.no_grad()
+def validate_same_sentence(args, refs, model, aux, local_rank=0):
+    """PRMS map selection (validate.py:253-387) with per-ref de-duplicated encoders."""
+    from tris_b200 import ops
+    model.eval()
+    eng = aux._engine()
+    ious, names = [], []
+    for idx, img, word_ids, target in refs:
+        img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
+        S = word_ids.shape[-1]
+        ids = word_ids[0].t().contiguous()                                     # [S, L]
+        c4 = model.image_features(img)
+        cams = torch.cat([model.respond(c4, ids[j:j + 1], img.shape[2:]) for j in range(S)])       # [S,1,H,W]
+        patches, _ = ops.mask_resize_fwd(cams, img.float().expand(S, -1, -1, -1).contiguous(), 224, 32)   # fg_j = cam_j * img
+        f = eng.encode_patches(patches, S).float()
+        g = eng.encode_text_hidden(ids).float()
+        f = f / f.norm(dim=-1, keepdim=True)
+        g = g / g.norm(dim=-1, keepdim=True)
+        best = int((f @ g.t()).sum(dim=1).argmax())                              # get_scores summed over the ref's sentences
+        cam = _to_original(cams[best:best + 1], target.shape[-2:])[0, 0]
+        iou, _, cam = _iou_hit(cam, target[0])
+        ious.append(iou)
+        if args.save_cam and args.cam_save_dir:
+            os.makedirs(args.cam_save_dir, exist_ok=True)
+            np.save(os.path.join(args.cam_save_dir, f"{idx}_{idx}.npy"), cam.cpu().numpy())      # {idx}_{img_id}.npy
+            names.append(f"{idx}_{idx}")
+    if args.save_cam and args.name_save_dir:
+        os.makedirs(args.name_save_dir, exist_ok=True)
+        json.dump(names, open(os.path.join(args.name_save_dir, f"{args.dataset}_train_names.json"), "w"))
+    return float(np.mean(ious)) if ious else 0.0
+
+
+def main(args):
+    warnings.simplefilter("ignore")
+    import time
+    from tris_b200 import clip_model as clip
+    from tris_b200 import dp
+    from tris_b200.model_stage1 import TRIS
+    rank, local, world = dp.env_rank()
+    torch.cuda.set_device(local)
+    if not args.synthetic:
+        raise SystemExit("validate.py: RefCOCO loaders are out of scope of this build (no dataset offline); use --synthetic")
+    model = TRIS(args).cuda()
+    if args.pretrain:
+        ck = torch.load(args.pretrain, map_location="cpu")
+        print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
+    refs = synthetic_refs(args, args.val_refs, rank, world)
+    t0 = time.time()
+    if args.prms:
+        aux, _ = clip.load("ViT-B/32", device="cuda", jit=False, txt_length=args.max_query_len)
+        miou = validate_same_sentence(args, refs, model, aux, rank)
+        torch.cuda.synchronize()
+        print(f"rank {rank}: PRMS mIoU {miou:.4f}  {len(dp.shard_range(args.val_refs, rank, world)) / (time.time() - t0):.1f} refs/s")
+    else:
+        miou, hit = validate(args, refs, model, rank)
+        torch.cuda.synchronize()
+        print(f"rank {rank}: mIoU {miou:.4f} hit {hit:.4f}  {len(dp.shard_range(args.val_refs, rank, world)) / (time.time() - t0):.1f} refs/s")
+
+
+if __name__ == "__main__":
+    main(get_parser().parse_args())
