@@ -224,10 +224,13 @@ def run_gpu_arm(a):
         e2e_step(i)
     ms_e2e = timed(e2e_step, a.steps)
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit conv): per-launch CUDA events in one eager step
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit conv): one CUDA-event pair per GEMM launch of one
+    # forward+backward; side-stream overlap is off for this pass so no other kernel shares the SMs with a timed GEMM.
     prof = None
     if rank == 0:
+        import tris_b200.engine as E
         saved_graph, trainer.graph = trainer.graph, None
+        saved_overlap, E.OVERLAP = E.OVERLAP, False
         gemm_calls = []
         orig = L.gemm_raw
 
@@ -237,21 +240,32 @@ def run_gpu_arm(a):
             orig(desc)
             e.record()
             taps = desc.taps if (desc.wgrad and desc.taps > 1) else 1
-            gemm_calls.append((s, e, 2.0 * desc.M * desc.N * desc.K * taps))
+            nb = max(1, desc.batch)
+            esz = 4 if desc.out_dtype == L.DT_F32 else 2
+            if desc.a_mode == L.OP_CONV and not desc.wgrad:       # activation read once (not once per tap) + weights + output
+                by = 2.0 * desc.M * (desc.K // max(1, desc.taps)) + 2.0 * desc.N * desc.K + esz * desc.M * desc.N
+            else:
+                by = 2.0 * desc.M * desc.K * (nb if desc.a_batch_stride else 1) + 2.0 * desc.N * desc.K * (nb if desc.b_batch_stride else 1) \
+                    + esz * desc.M * desc.N * taps * nb
+            gemm_calls.append((s, e, 2.0 * desc.M * desc.N * desc.K * taps * nb, by))
 
         L.gemm_raw = timed_gemm
         gemm.L.gemm_raw = timed_gemm
-        # queue the whole eager step behind a ~60 ms spin kernel so that every launch is already enqueued when the GPU
-        # reaches it: the per-launch event pairs then measure kernel durations, not Python launch gaps
-        torch.cuda._sleep(int(1.2e8))
-        trainer.step(*dev[0])
+        # queue the whole eager pass behind a ~100 ms spin kernel so that the launches are already enqueued when the GPU
+        # reaches them: the per-launch event pairs then measure kernel durations rather than Python launch gaps
+        how = "CUDA-event pair per launch, eager fwd+bwd queued behind a 100 ms spin kernel, side-stream overlap off"
         torch.cuda.synchronize()
+        torch.cuda._sleep(int(2.0e8))
+        trainer._fwd_bwd(*dev[0])
+        torch.cuda.synchronize()
+        t_ms = sum(c[0].elapsed_time(c[1]) for c in gemm_calls)
         L.gemm_raw = orig
         gemm.L.gemm_raw = orig
         trainer.graph = saved_graph
-        t_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_calls)
-        fl = sum(f for _, _, f in gemm_calls)
-        prof = {"launches": len(gemm_calls), "ms": t_ms, "tflops": fl / (t_ms * 1e-3) / 1e12, "gflop": fl / 1e9}
+        E.OVERLAP = saved_overlap
+        fl = sum(c[2] for c in gemm_calls)
+        prof = {"launches": len(gemm_calls), "ms": t_ms, "tflops": fl / (t_ms * 1e-3) / 1e12, "gflop": fl / 1e9, "how": how,
+                "bytes": sum(c[3] for c in gemm_calls)}
 
     # ---- cross-modal attention group (K6 tail + K7 + K8: north-star "attn HBM GB/s"): forward of the head on resident
     # c4 / hidden, one CUDA-event pair per repetition, L2 flushed (256 MB write) between repetitions
@@ -282,6 +296,11 @@ def run_gpu_arm(a):
             dist.destroy_process_group()
         return
     sust, burst, hbm, src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.exists(tpath) and B == 48:
+        tj = json.load(open(tpath))
+        traffic = tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]
     sps = B * world * a.steps / (ms * 1e-3)
     sps_e2e = B * world * a.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -304,7 +323,9 @@ def run_gpu_arm(a):
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": prof["tflops"], "peak": sust, "unit": "TFLOP/s", "frac": prof["tflops"] / sust,
-                     "traffic": None, "kernel": "tris_umma_gemm_kernel", "peak_source": f"{src} sustained bf16",
+                     "traffic": traffic, "traffic_unit": "bytes per step (all GEMM launches, ncu dram__bytes_read+write, profiles/r1_gemm_traffic.json)",
+                     "algorithmic_bytes": prof["bytes"],
+                     "kernel": "tris_umma_gemm_kernel", "peak_source": f"{src} sustained bf16", "timing": prof["how"],
                      "launches_per_step": prof["launches"], "kernel_ms_per_step": prof["ms"], "kernel_gflop_per_step": prof["gflop"],
                      "kernel_share_of_step": prof["ms"] / (ms / a.steps),
                      "step_frac_of_peak": (GFLOP_PER_SAMPLE * 1e9 * sps / world) / (sust * 1e12)},

@@ -13,6 +13,12 @@ which = sys.argv[1]
 if which == "conv":
     dy = rnd(48, 80, 80, 64); wp = rnd(64, 576); dx = torch.empty(48, 80, 80, 64, device="cuda", dtype=bf16)
     fn = lambda: G.conv3x3_dgrad(dy, wp, 64, out=dx)
+elif which == "small":
+    x, w = rnd(960, 512), rnd(512, 512); o = torch.empty(960, 512, device="cuda", dtype=bf16)
+    fn = lambda: G.linear_fwd(x, w, out=o)
+elif which == "mid":
+    x, w = rnd(2400, 768), rnd(3072, 768); o = torch.empty(2400, 3072, device="cuda", dtype=bf16)
+    fn = lambda: G.linear_fwd(x, w, out=o)
 else:
     x, w = rnd(307200, 256), rnd(64, 256); o = torch.empty(307200, 64, device="cuda", dtype=bf16)
     fn = lambda: G.linear_fwd(x, w, out=o)

@@ -11,11 +11,11 @@ timeout 300 python train_stage1.py --synthetic --batch_size 48 --size 320 --max_
 timeout 300 python validate.py --synthetic --size 320 --max_query_len 20 --val_refs 200 > gpurun_out/validate_entry.txt 2>&1; tail -2 gpurun_out/validate_entry.txt
 timeout 300 python validate.py --synthetic --size 320 --max_query_len 20 --val_refs 200 --prms >> gpurun_out/validate_entry.txt 2>&1; tail -1 gpurun_out/validate_entry.txt
 timeout 120 python demo.py --synthetic --output gpurun_out/demo_cam.npy > gpurun_out/demo_entry.txt 2>&1; tail -1 gpurun_out/demo_entry.txt
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
-python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launch_summary.txt 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches.csv gpurun_out/gemm_traffic.json > gpurun_out/launch_summary.txt 2>&1
 head -30 gpurun_out/launch_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tris_umma_gemm_kernel -s 60 -c 3 -o gpurun_out/prof_gemm python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:bn_bwd_apply -s 20 -c 1 -o gpurun_out/prof_bn python tools/profile_step.py >> gpurun_out/ncu_full.log 2>&1
+rm -f gpurun_out/prof_targets.ncu-rep
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_targets python tools/ncu_targets.py > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 REPS=3 timeout 300 python tools/bench_gemm_shapes.py > gpurun_out/gemm_shapes.txt 2>&1; cat gpurun_out/gemm_shapes.txt
 fi

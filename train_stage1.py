@@ -47,8 +47,10 @@ def main(args):
     trainer = Stage1Trainer(model, aux, max_iter=max_iter, lr=args.lr, lr_multi=args.lr_multi, weight_decay=args.weight_decay,
                             w=(args.w1, args.w4, args.w5))
     B, k = args.batch_size, args.negative_samples
-    batch = lambda i: tuple(None if t is None else t.cuda(non_blocking=True)
-                            for t in synthetic_batch(B, args.size, args.max_query_len, k, seed=dp.shard_seed(1234, rank, i), pin=True))
+    # a small pool of pinned synthetic batches, re-used round-robin (generating 48 x 3 x 320 x 320 normals on the host costs
+    # more than the whole GPU step); each step still pays the H2D copy like a real DataLoader(pin_memory=True) batch
+    pool = [synthetic_batch(B, args.size, args.max_query_len, k, seed=dp.shard_seed(1234, rank, i), pin=True) for i in range(4)]
+    batch = lambda i: tuple(None if t is None else t.cuda(non_blocking=True) for t in pool[i % len(pool)])
     if not args.no_graph:
         trainer.capture(*batch(0), warmup=1)
     best = -1.0

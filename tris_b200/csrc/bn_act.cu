@@ -436,7 +436,7 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // cap the reduction grid: each block ends with 2-4 * C atomics
     int rgrid = grid_for(total);
-    if (rgrid > 2 * tris::sm_count()) rgrid = 2 * tris::sm_count();
+    if (rgrid > 4 * tris::sm_count()) rgrid = 4 * tris::sm_count();   // 4 resident CTAs/SM (64 registers/thread)
     const size_t rsmem = (4 * c + kThreads * 8) * sizeof(float), asmem = 7 * c * sizeof(float);
     static bool attr = false;
     if (!attr) {

@@ -159,7 +159,49 @@ class ResNetTower:
 
     # ------------------------------------------------------------------ backward
     def backward(self, tape, dout: torch.Tensor):
-        """dout: gradient w.r.t. c4 (bf16 NHWC).  Writes all parameter gradients into the store."""
+        """dout: gradient w.r.t. c4 (bf16 NHWC).  Writes all parameter gradients into the store.
+
+        Weight gradients are leaves of the backward chain: they are issued on a side stream (``_wg``) so that these
+        tensor-core GEMMs run next to the HBM-bound BatchNorm-backward kernels of the following layer instead of in
+        front of them.  The side stream joins the main stream at the end."""
+        st, p = self.store, self.prefix
+        self._wg_begin()
+        try:
+            self._backward(tape, dout)
+        finally:
+            self._wg_end()
+
+    # ---- weight-gradient side stream
+    def _wg_begin(self):
+        from .engine import OVERLAP
+        self._wg_stream = None
+        if OVERLAP:
+            if not hasattr(self, "_wg_side"):
+                self._wg_side = torch.cuda.Stream()
+            self._wg_stream = self._wg_side
+            self._wg_main = torch.cuda.current_stream()
+            self._wg_stream.wait_stream(self._wg_main)
+            self._wg_keep = []
+
+    def _wg_end(self):
+        if self._wg_stream is not None:
+            self._wg_main.wait_stream(self._wg_stream)
+            self._wg_keep = []
+            self._wg_stream = None
+
+    def _wg(self, fn, *tensors):
+        """Run fn() (a weight-gradient launch sequence reading `tensors`) on the side stream after everything issued so
+        far on the main stream; the operands are kept alive until the join."""
+        if getattr(self, "_wg_stream", None) is None:
+            return fn()
+        self._wg_stream.wait_stream(self._wg_main)
+        for t in tensors:
+            t.record_stream(self._wg_stream)
+        self._wg_keep.extend(tensors)
+        with torch.cuda.stream(self._wg_stream):
+            fn()
+
+    def _backward(self, tape, dout):
         st, p = self.store, self.prefix
         for blk in reversed(self.blocks):
             dout = self._block_bwd(blk, tape[blk.p], dout)
@@ -175,21 +217,26 @@ class ResNetTower:
         pb1 = self.pad_bn[p + "bn1"]
         pb1.dgamma.zero_(); pb1.dbeta.zero_()
         dy1, _, _ = ops.bn_bwd(da1, None, y1, pb1)
-        gw = G.linear_wgrad(dy1.view(-1, 64), col)                       # [64, 64] fp32
-        g1 = st.g(p + "conv1.weight")                                    # [32,3,3,3]
-        g1.add_(gw[:32, :27].reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+        def stem1():
+            gw = G.linear_wgrad(dy1.view(-1, 64), col)                   # [64, 64] fp32
+            g1 = st.g(p + "conv1.weight")                                # [32,3,3,3]
+            g1.add_(gw[:32, :27].reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+        self._wg(stem1, dy1, col)
         for nm, pad in (("bn1", pb1), ("bn2", pb2)):
             st.g(p + nm + ".weight").add_(pad.dgamma[:32])
             st.g(p + nm + ".bias").add_(pad.dbeta[:32])
 
     def _wgrad3x3(self, dy, x, key, ci_pad=None):
         gw = self.store.g(key)
-        gp = G.conv3x3_wgrad(dy, x)
-        ops.unpack_conv_grad(gp, gw, ci_pad=ci_pad)
+
+        def run():
+            gp = G.conv3x3_wgrad(dy, x)
+            ops.unpack_conv_grad(gp, gw, ci_pad=ci_pad)
+        self._wg(run, dy, x)
 
     def _wgrad1x1(self, dy2d, x2d, key):
         gw = self.store.g(key)
-        G.linear_wgrad(dy2d, x2d, out=gw.view(gw.shape[0], gw.shape[1]), accumulate=True)
+        self._wg(lambda: G.linear_wgrad(dy2d, x2d, out=gw.view(gw.shape[0], gw.shape[1]), accumulate=True), dy2d, x2d)
 
     def _block_bwd(self, blk: _Block, rec, dout):
         x, y1, a1, y2, a2, y3, xp, yd, out = rec
