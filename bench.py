@@ -210,9 +210,15 @@ def run_gpu_arm(a):
 
     dev_step = lambda i: trainer.step(*dev[i % n_pool])
 
+    from tris_b200.train_step import HostBatchPrefetcher
+    pf = HostBatchPrefetcher()
+    pf.submit(host[0])
+
     def e2e_step(i):
-        hb = host[i % n_pool]
-        out = trainer.step(*(t.cuda(non_blocking=True) for t in hb))
+        # public trainer API with pinned HOST batches: every step issues the H2D copy of one full batch (the next one, on
+        # the copy stream, while this step computes) and reads the loss back to the host
+        out = trainer.step(*pf.take())
+        pf.submit(host[(i + 1) % n_pool])
         return out["loss"].item()
 
     for i in range(a.warmup):
@@ -223,6 +229,7 @@ def run_gpu_arm(a):
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, a.steps)
+    pf.take()
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit conv): one CUDA-event pair per GEMM launch of one
     # forward+backward; side-stream overlap is off for this pass so no other kernel shares the SMs with a timed GEMM.

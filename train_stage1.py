@@ -29,7 +29,7 @@ def main(args):
     from tris_b200 import dp
     from tris_b200.model_stage1 import TRIS
     from tris_b200.synthetic import synthetic_batch
-    from tris_b200.train_step import Stage1Trainer
+    from tris_b200.train_step import HostBatchPrefetcher, Stage1Trainer
     import validate as V
     rank, local, world = dp.env_rank()
     torch.cuda.set_device(local)
@@ -53,11 +53,15 @@ def main(args):
     batch = lambda i: tuple(None if t is None else t.cuda(non_blocking=True) for t in pool[i % len(pool)])
     if not args.no_graph:
         trainer.capture(*batch(0), warmup=1)
+    pf = HostBatchPrefetcher()
+    pf.submit(pool[0])
     best = -1.0
     for epoch in range(args.start_epoch, args.epoch):
         t0, seen = time.time(), 0
         for it in range(args.steps_per_epoch):
-            losses = trainer.step(*batch(epoch * args.steps_per_epoch + it))
+            dev = pf.take()
+            pf.submit(pool[(epoch * args.steps_per_epoch + it + 1) % len(pool)])      # H2D of the next batch under this step
+            losses = trainer.step(*dev)
             seen += B * world
             if rank == 0 and (it + 1) % args.print_freq == 0 or it + 1 == args.steps_per_epoch:
                 vals = {k_: float(v) for k_, v in losses.items()}        # one host sync per print, not per step

@@ -227,6 +227,22 @@ __device__ __forceinline__ void softmax_rows(float* s, float* ds, int L, bool bw
     }
 }
 
+// One head's L x 64 slice of a row-major bf16 matrix -> fp32 smem [L][HDP], 128-bit loads (8 vectors per row).
+__device__ __forceinline__ void load_head_rows(const __nv_bfloat16* __restrict__ base, long row_stride, int L, float* dst, float scale) {
+    for (int i = threadIdx.x; i < L * 8; i += blockDim.x) {
+        const int l = i >> 3, vv = i & 7;
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + l * row_stride) + vv);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+        float* d = dst + l * HDP + vv * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            d[2 * j] = f.x * scale;
+            d[2 * j + 1] = f.y * scale;
+        }
+    }
+}
+
 template <bool BWD>
 __device__ __forceinline__ void score_tiles(const float* q, const float* k, const float* go, const float* v, float* s, float* ds,
                                             int L, int causal) {
@@ -280,13 +296,10 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __re
     const int n = blockIdx.x / heads, h = blockIdx.x % heads;
     const int D = heads * HD;
     const long row0 = static_cast<long>(n) * L;
-    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
-        const int l = i / HD, d = i % HD;
-        const __nv_bfloat16* r = qkv + (row0 + l) * 3 * D + h * HD + d;
-        q[l * HDP + d] = __bfloat162float(r[0]) * 0.125f;   // 1/sqrt(64)
-        k[l * HDP + d] = __bfloat162float(r[D]);
-        v[l * HDP + d] = __bfloat162float(r[2 * D]);
-    }
+    const __nv_bfloat16* base = qkv + row0 * 3 * D + h * HD;
+    load_head_rows(base, 3L * D, L, q, 0.125f);   // 1/sqrt(64)
+    load_head_rows(base + D, 3L * D, L, k, 1.f);
+    load_head_rows(base + 2 * D, 3L * D, L, v, 1.f);
     __syncthreads();
     score_tiles<false>(q, k, nullptr, nullptr, s, nullptr, L, causal);
     __syncthreads();
@@ -335,14 +348,11 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const __nv_bfloat16* __re
     const int n = blockIdx.x / heads, h = blockIdx.x % heads;
     const int D = heads * HD;
     const long row0 = static_cast<long>(n) * L;
-    for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
-        const int l = i / HD, d = i % HD;
-        const __nv_bfloat16* r = qkv + (row0 + l) * 3 * D + h * HD + d;
-        q[l * HDP + d] = __bfloat162float(r[0]) * 0.125f;
-        k[l * HDP + d] = __bfloat162float(r[D]);
-        v[l * HDP + d] = __bfloat162float(r[2 * D]);
-        go[l * HDP + d] = __bfloat162float(dout[(row0 + l) * D + h * HD + d]);
-    }
+    const __nv_bfloat16* base = qkv + row0 * 3 * D + h * HD;
+    load_head_rows(base, 3L * D, L, q, 0.125f);
+    load_head_rows(base + D, 3L * D, L, k, 1.f);
+    load_head_rows(base + 2 * D, 3L * D, L, v, 1.f);
+    load_head_rows(dout + row0 * D + h * HD, D, L, go, 1.f);
     __syncthreads();
     score_tiles<true>(q, k, go, v, s, ds, L, causal);
     __syncthreads();
@@ -544,7 +554,10 @@ int tris_scatter_rows(const void* src, const int* idx, void* out, int rows, int 
 }
 
 int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream) {
-    dim3 grid((N + 63) / 64, rows >= 2048 ? 32 : (rows >= 256 ? 8 : 1));
+    int chunks = (rows + 31) / 32;   // <= 8 rows per thread: the row loop is a chain of dependent-latency loads
+    if (chunks > 128) chunks = 128;
+    if (chunks < 1) chunks = 1;
+    dim3 grid((N + 63) / 64, chunks);
     colsum_kernel<<<grid, dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, N);
     TRIS_LAUNCH_OK("colsum_kernel");
     return TRIS_OK;

@@ -9,6 +9,7 @@ learning-rate groups and the per-step poly-0.9 schedule).  Differences, all deli
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -34,21 +35,29 @@ def stage1_losses(model, aux, img, word_ids, neg_word_ids, w1=1.0, w4=5.0, w5=2.
     eng = aux._engine()
     k = 0 if neg_word_ids is None else neg_word_ids.shape[1]
     ids = word_ids if k == 0 else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
-    if OVERLAP:
-        # the frozen text tower depends on the token ids only: it runs on a side stream under the RN50 forward
-        main, side = torch.cuda.current_stream(), eng.side_stream()
+    late = os.environ.get("TRIS_AUX_TEXT_LATE", "1") != "0"
+    main, side = torch.cuda.current_stream(), eng.side_stream()
+
+    def fork_text():
+        # the frozen text tower depends on the token ids only: it runs on a side stream next to other work
         eng.ensure_fresh()
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            g = eng.encode_text_hidden(ids)
-    else:
-        g = eng.encode_text_hidden(ids)
+            return eng.encode_text_hidden(ids)
+
+    g = None
+    if OVERLAP and not late:
+        g = fork_text()                       # under the RN50 forward
     cls, _, _, sig_out, _ = model(img, word_ids)
+    if OVERLAP and late:
+        g = fork_text()                       # under the frozen ViT forward (both are small-kernel chains)
     patches = masked_patches(sig_out, img)
+    if not OVERLAP:
+        g = eng.encode_text_hidden(ids)
+    f = eng.encode_patches(patches, B)
     if OVERLAP:
         main.wait_stream(side)
         g.record_stream(main)
-    f = eng.encode_patches(patches, B)
     loss, l1, l4, l5 = stage1_loss(f, g, cls, k, (w1, w4, w5))
     return {"loss": loss, "l1": l1, "l4": l4, "l5": l5}
 
@@ -124,3 +133,28 @@ class Stage1Trainer:
             out = self._step_eager(s_img, s_ids, s_neg) if self.world == 1 else self._fwd_bwd(s_img, s_ids, s_neg)
         self.graph, self.static = g, (s_img, s_ids, s_neg, out)
         return self
+
+
+class HostBatchPrefetcher:
+    """Pinned-host -> device pipeline for the training loop: the H2D copy of batch i+1 is issued on a copy stream while
+    step i computes (what DataLoader(pin_memory=True) + .cuda(non_blocking=True) gives the reference loop,
+    train_stage1.py:118-123,302-316, when the copy is issued ahead of the step)."""
+
+    def __init__(self):
+        self.stream = torch.cuda.Stream()
+        self._next = None
+
+    def submit(self, host_batch):
+        """Start copying a pinned host batch (tuple of tensors / None)."""
+        with torch.cuda.stream(self.stream):        # fresh device buffers each time: nothing to wait for
+            self._next = tuple(None if t is None else t.cuda(non_blocking=True) for t in host_batch)
+
+    def take(self):
+        """Device batch submitted last; the current stream waits for its copy."""
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream)
+        out, self._next = self._next, None
+        for t in out:
+            if t is not None:
+                t.record_stream(cur)
+        return out
