@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace {
@@ -455,6 +457,17 @@ __global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ patch, con
 
 }  // namespace
 
+namespace tris {
+int attn_fwd_mma(const void* qkv, void* out, int n, int L, int heads, int causal, cudaStream_t stream);
+int attn_bwd_mma(const void* qkv, const void* dout, void* dqkv, int n, int L, int heads, int causal, cudaStream_t stream);
+}
+// TRIS_ATTN_FP32=1 selects the register-tiled fp32 CUDA-core kernels below instead of the tensor-core ones (attn_small.cu).
+static bool use_fp32_attention() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TRIS_ATTN_FP32"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 extern "C" {
 
 int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D, tris_stream_t stream) {
@@ -515,6 +528,7 @@ static size_t attn_smem(int L, bool bwd) {
 }
 
 int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causal, tris_stream_t stream) {
+    if (L >= 1 && L <= 64 && !use_fp32_attention()) return tris::attn_fwd_mma(qkv, out, n, L, heads, causal, reinterpret_cast<cudaStream_t>(stream));
     if (L > 64 || L < 1) return tris::fail(TRIS_ERR_SHAPE, "tris_attn_fwd: L=%d must be in 1..64", L);
     static bool attr = false;
     if (!attr) { TRIS_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
@@ -525,6 +539,7 @@ int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causa
 }
 
 int tris_attn_bwd(const void* qkv, const void* dout, void* dqkv, int n, int L, int heads, int causal, tris_stream_t stream) {
+    if (L >= 1 && L <= 64 && !use_fp32_attention()) return tris::attn_bwd_mma(qkv, dout, dqkv, n, L, heads, causal, reinterpret_cast<cudaStream_t>(stream));
     if (L > 64 || L < 1) return tris::fail(TRIS_ERR_SHAPE, "tris_attn_bwd: L=%d must be in 1..64", L);
     static bool attr = false;
     if (!attr) { TRIS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024)); attr = true; }
