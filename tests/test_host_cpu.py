@@ -92,7 +92,7 @@ def test_gemm_tiling_heuristics():
     for n in (48, 64, 512, 3072):
         assert G._bn_for(n, 38) in (32, 64, 128, 256)
     assert G._bn_for(24, 8) == 32 and G._bn_for(24, 8, True) == 64
-    assert G._split_for(200, 100) == 1 and G._split_for(8, 4800) > 1
+    assert G._split_for(400, 100) == 1 and G._split_for(8, 4800) > 1
 
 
 def test_clip_load_aliases():

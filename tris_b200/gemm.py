@@ -83,10 +83,19 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
 
 
 def _split_for(tiles: int, kblocks: int) -> int:
-    if tiles >= SMS:
+    """Split-K factor for a weight-gradient GEMM with `tiles` output tiles and `kblocks` k-blocks: minimise
+    waves(148 SMs) x k-blocks per work unit (+ a small per-unit cost for prologue / fp32 reduce-add epilogue)."""
+    if tiles >= 2 * SMS:
         return 1
-    s = (2 * SMS + tiles - 1) // tiles
-    return max(1, min(s, max(1, kblocks // 4)))
+    best, best_cost = 1, None
+    for sk in range(1, max(1, min(kblocks // 2, 4 * SMS // max(1, tiles) + 1)) + 1):
+        per = (kblocks + sk - 1) // sk
+        units = tiles * ((kblocks + per - 1) // per)
+        waves = (units + SMS - 1) // SMS
+        cost = waves * (per + 6)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = sk, cost
+    return best
 
 
 def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
