@@ -50,7 +50,7 @@ def main(args):
     from tris_b200 import ops
     from tris_b200.model_stage1 import TRIS
     img, ids, (h, w) = prepare(args)
-    model = TRIS(args).cuda().eval()
+    model = TRIS(args).cuda().set_precision(args.precision).eval()
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
         print("load:", model.load_state_dict(ck.get("model", ck), strict=False))

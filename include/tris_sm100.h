@@ -215,6 +215,33 @@ int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream
 int tris_vit_assemble(const void* patch, const float* cls, const float* pos, void* tok, int n, int T, int D,
     tris_stream_t stream);
 
+/* ---- precise.cu: fp32 parity mode (forward only, CUDA cores; all buffers fp32; BatchNorm batch sums fp64).  Same reference lines
+ * as the bf16 kernels above: convolutions as im2col + SGEMM, BatchNorm train/eval + ReLU + residual, AvgPool2d(2), embedding, LayerNorm,
+ * attention, L2 / InstanceNorm / softmax / 0.1-mix of the fusion. */
+int tris_sgemm(const float* A, const float* B, float* C, const float* bias, const float* res, int M, int N, int K,
+    int lda, int ldb, int ldc, int b_kn, int act, float alpha, int batch, long sa, long sb, long sc, tris_stream_t
+    stream);
+int tris_im2col3x3_f32(const float* x, float* col, int n, int h, int w, int c, int stride, int nchw, tris_stream_t
+    stream);
+int tris_colstats_f32(const float* x, double* stats, long rows, int c, tris_stream_t stream);
+int tris_bn_f32(const float* y0, const double* stats0, const float* gamma0, const float* beta0, const float* rm0,
+    const float* rv0, const float* y1, const double* stats1, const float* gamma1, const float* beta1, const float*
+    rm1, const float* rv1, const float* res, float* out, long rows, int c, int relu, float eps, tris_stream_t
+    stream);
+int tris_avgpool2_f32(const float* x, float* out, int n, int h, int w, int c, tris_stream_t stream);
+int tris_embed_f32(const int* ids, const float* E, const float* P, float* x, int* eot, int n, int L, int D,
+    tris_stream_t stream);
+int tris_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int D, float eps,
+    tris_stream_t stream);
+int tris_attn_f32(const float* qkv, float* out, int n, int L, int heads, int causal, tris_stream_t stream);
+int tris_gather_rows_f32(const float* x, const int* idx, float* out, int rows, int D, tris_stream_t stream);
+int tris_l2norm_f32(const float* x, float* y, int rows, int D, tris_stream_t stream);
+int tris_instnorm_f32(const float* x, const float* gamma, const float* beta, const float* mix_add, float* out, int
+    batch, int P, int C, float mix_scale, int relu, float eps, tris_stream_t stream);
+int tris_softmax_f32(const float* x, float* y, int rows, int n, int ld, float scale, tris_stream_t stream);
+int tris_bcast_mix_f32(const float* base, const float* x, float* out, long per, int B, float a, tris_stream_t
+    stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,7 +37,16 @@ class TRIS(nn.Module):
         S.build_tree(self, entries)
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self._eng = None
+        self.precision = "bf16"
         self.train()
+
+    def set_precision(self, precision: str):
+        """"bf16" (default): tcgen05 bf16 path, forward + backward.  "fp32": forward-only parity mode in full fp32
+        (tris_b200/precise.py) for checking response maps against the reference at 1e-3."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        return self
 
     def trainable_parameters(self):
         new = [self.vis_project, self.lan_project]
@@ -64,6 +73,11 @@ class TRIS(nn.Module):
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError(f"x must be [B,3,H,W] with H,W multiples of 32, got {tuple(x.shape)}")
         eng = self.engine()
+        if self.precision == "fp32":
+            if self.training and torch.is_grad_enabled():
+                raise L.TrisLibError("precision='fp32' is a forward-only parity mode: call it under torch.no_grad()")
+            from .precise import PreciseStage1
+            return PreciseStage1(self).forward(x, word_id, self.training)
         c4, hidden = eng.towers(x, word_id, self.training)
         out = eng.head.forward(c4, hidden, tuple(x.shape[2:]), self.training)
         return out if self.training else out[0]

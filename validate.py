@@ -116,7 +116,7 @@ def main(args):
     torch.cuda.set_device(local)
     if not args.synthetic:
         raise SystemExit("validate.py: RefCOCO loaders are out of scope of this build (no dataset offline); use --synthetic")
-    model = TRIS(args).cuda()
+    model = TRIS(args).cuda().set_precision(args.precision)
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
         print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
