@@ -102,7 +102,7 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
 int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* gamma0, const float* beta0, const
     float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0, const void* y1, const
     float* gamma1, const float* beta1, const float* save_mean1, const float* save_invstd1, float* dgamma1, float*
-    dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, tris_stream_t stream);
+    dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, int fold_half, tris_stream_t stream);
 /* nn.AvgPool2d(2) on NHWC bf16 (the anti-aliased stride of the downsample branch, model.py:37). */
 int tris_avgpool2_fwd(const void* x, void* out, int n, int h, int w, int c, tris_stream_t stream);
 /* its adjoint (+ optional accumulate source). */
@@ -154,6 +154,12 @@ int tris_stage1_loss_bwd(const void* f, const void* g, const float* cls, const f
 /* ---- misc.cu */
 /* data movement of the stride-2 3x3 stem conv on the fp32 NCHW image (model.py:212-217,255-258). */
 int tris_stem_im2col(const float* img, void* col, int n, int h, int w, tris_stream_t stream);
+/* pair-packed stem (two images per 64-channel row, block-diagonal weights): im2col of an image pair, block-diagonal weight packing /
+ * gradient un-packing, and the fold of per-channel statistics of the two halves. */
+int tris_stem_im2col_pair(const float* img, void* col, int n, int h, int w, tris_stream_t stream);
+int tris_pack_conv_blockdiag(const float* w, void* out, int co, int ci, int khw, int reps, tris_stream_t stream);
+int tris_unpack_conv_grad_blockdiag(const float* gp, float* gw, int co, int ci, int khw, int reps, tris_stream_t stream);
+int tris_fold_pairs(float* a, float* b, float* c, int half, tris_stream_t stream);
 /* fp32 master -> bf16 operand copy of all parameters. */
 int tris_f32_to_bf16(const float* src, void* dst, long n, tris_stream_t stream);
 /* OIHW fp32 -> [Cout, taps*Cin] bf16 (tap-major K) for the implicit-GEMM convs. */

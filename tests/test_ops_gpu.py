@@ -376,3 +376,44 @@ def test_bottleneck_block_fwd_bwd_vs_oracle(tris, name, hw):
     for k, v in errs.items():
         assert v < 0.12, (k, v)
     m.load_state_dict(sdb, strict=False)
+
+
+def test_pair_packed_stem_matches_padded_stem(tris):
+    """Even batches run the stem with two images per 64-channel row (block-diagonal weights, folded BatchNorm sums);
+    it must agree with the zero-padded form used for odd batches: stem output, stem parameter gradients, running stats.
+    (Stem in isolation: through the whole random-init tower at a tiny batch the comparison would be chaotic.)"""
+    m, eng, sd = tris
+    rn = eng.resnet
+    img = torch.randn(4, 3, 128, 128, generator=torch.Generator().manual_seed(11)).cuda()
+    dx = (torch.randn(4, 32, 32, 64, generator=torch.Generator().manual_seed(12)) * 0.1).cuda().to(bf16)
+    p = "backbone.visual."
+    keys = [p + k for k in ("conv1.weight", "bn1.weight", "bn1.bias", "conv2.weight", "bn2.weight", "bn2.bias", "conv3.weight",
+                            "bn3.weight", "bn3.bias")]
+    bufs = dict(m.named_buffers())
+    res = {}
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    for pair in (False, True):
+        m.load_state_dict(sd0)
+        eng.ensure_fresh(True)
+        eng.store.zero_grad()
+        rn.stats_buf.zero_()
+        off = [0]
+
+        def stats(c):
+            s_ = rn.stats_buf[off[0]: off[0] + 2 * c]
+            off[0] += 2 * c
+            return s_
+        x, rec = (rn._stem_fwd_pair if pair else rn._stem_fwd_padded)(img, True, stats)
+        rn._stem_bwd((pair,) + rec, dx.clone())
+        torch.cuda.synchronize()
+        res[pair] = (x.float().clone(), {k: eng.store.g(k).clone() for k in keys},
+                     {k: bufs[k].clone() for k in (p + "bn1.running_mean", p + "bn2.running_var", p + "bn3.running_var")})
+    m.load_state_dict(sd0)
+    e_x = frob(res[True][0], res[False][0])
+    errs = {k: frob(res[True][1][k], res[False][1][k]) for k in keys}
+    print("stem out", e_x, errs)
+    assert e_x < 1e-2
+    for k, e in errs.items():
+        assert e < 3e-2, (k, e)
+    for k, v in res[True][2].items():
+        assert rel(v, res[False][2][k]) < 2e-3, k

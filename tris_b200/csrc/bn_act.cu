@@ -416,7 +416,7 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
                 const float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0,
                 const void* y1, const float* gamma1, const float* beta1, const float* save_mean1,
                 const float* save_invstd1, float* dgamma1, float* dbeta1, void* dy1, void* g_out, int n, int h, int w,
-                int c, int pool, int relu, tris_stream_t stream) {
+                int c, int pool, int relu, int fold_half, tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_bwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: pool must be 1 or 2");
     BwdParams p{};
@@ -447,6 +447,9 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     if (y1 != nullptr) bn_bwd_reduce_kernel<true><<<rgrid, kThreads, rsmem, s>>>(p);
     else bn_bwd_reduce_kernel<false><<<rgrid, kThreads, rsmem, s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
+    if (fold_half > 0) {   // pair-packed stem: channels c and c + fold_half are one BatchNorm channel
+        if (int e = tris_fold_pairs(dgamma0, dbeta0, nullptr, fold_half, stream)) return e;
+    }
     if (y1 != nullptr) bn_bwd_apply_kernel<true><<<grid_for(total), kThreads, asmem, s>>>(p);
     else bn_bwd_apply_kernel<false><<<grid_for(total), kThreads, asmem, s>>>(p);
     TRIS_LAUNCH_OK("bn_bwd_apply_kernel");

@@ -69,6 +69,90 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(n4 << 2) + threadIdx.x] = __float2bfloat16(src[(n4 << 2) + threadIdx.x]);
 }
 
+// Image-pair-packed variant (stem, resnet.py): row = pixel of the image PAIR (2i, 2i+1); columns 0..26 = patch of image
+// 2i, 32..58 = patch of image 2i+1, rest zero.  The 32-channel stem activations then carry two images in one 64-channel
+// row (full 128-byte TMA rows with no padding) and the stem convs use block-diagonal weights.
+__global__ void __launch_bounds__(256) stem_im2col_pair_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ col,
+                                                               int N2, int H, int W) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long total = static_cast<long>(N2) * Ho * Wo * 2;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int half = static_cast<int>(i & 1);
+        const long pix = i >> 1;
+        const int wo = static_cast<int>(pix % Wo);
+        const long t = pix / Wo;
+        const int ho = static_cast<int>(t % Ho);
+        const long n = (t / Ho) * 2 + half;
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hi = 2 * ho + r - 1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int wi = 2 * wo + q - 1;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[(r * 3 + q) * 3 + c] = __ldg(img + ((n * 3 + c) * H + hi) * W + wi);
+                }
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(col + pix * 64 + half * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            dst[g] = o;
+        }
+    }
+}
+
+// OIHW fp32 [co, ci, kh, kw] -> bf16 block-diagonal [reps*co, khw * reps*ci]: block (r, r) = the packed weight, rest zero.
+__global__ void pack_conv_blockdiag_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int co, int ci, int khw, int reps) {
+    const int CI = reps * ci;
+    const long total = static_cast<long>(reps) * co * khw * CI;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int cc = static_cast<int>(i % CI);
+        const long t = i / CI;
+        const int tap = static_cast<int>(t % khw);
+        const int oo = static_cast<int>(t / khw);
+        const int ro = oo / co, o = oo % co, rc = cc / ci, c = cc % ci;
+        out[i] = __float2bfloat16(ro == rc ? w[(static_cast<long>(o) * ci + c) * khw + tap] : 0.f);
+    }
+}
+// gw[o, c, tap] += sum_r gp[(r*co + o), tap, r*ci + c]    (gp fp32 [reps*co, khw * reps*ci])
+__global__ void unpack_conv_grad_blockdiag_kernel(const float* __restrict__ gp, float* __restrict__ gw, int co, int ci, int khw, int reps) {
+    const long total = static_cast<long>(co) * ci * khw;
+    const int CI = reps * ci;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(i % khw);
+        const long t = i / khw;
+        const int c = static_cast<int>(t % ci);
+        const int o = static_cast<int>(t / ci);
+        float s = 0.f;
+        for (int r = 0; r < reps; ++r) s += gp[(static_cast<long>(r * co + o) * khw + tap) * CI + r * ci + c];
+        gw[i] += s;
+    }
+}
+// a[c] = a[c + half] = (a[c] + a[c + half]) / 2 for c < half, on up to three arrays (statistics of channels that are the
+// same BatchNorm channel in the pair-packed layout)
+__global__ void fold_pairs_kernel(float* a, float* b, float* c3, int half) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    float* arr[3] = {a, b, c3};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (arr[k] != nullptr) {
+            const float m = 0.5f * (arr[k][i] + arr[k][i + half]);
+            arr[k][i] = m;
+            arr[k][i + half] = m;
+        }
+    }
+}
+
 // OIHW fp32 [co, ci, kh, kw] -> bf16 [co_pad, kh*kw*ci_pad] with k = (r*kw+s)*ci_pad + c (zero padding)
 __global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int co, int ci, int khw, int co_pad,
                                  int ci_pad) {
@@ -262,6 +346,34 @@ int tris_stem_im2col(const float* img, void* col, int n, int h, int w, tris_stre
     stem_im2col_kernel<<<grid1d(static_cast<long>(n) * (h / 2) * (w / 2)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         img, reinterpret_cast<__nv_bfloat16*>(col), n, h, w);
     TRIS_LAUNCH_OK("stem_im2col_kernel");
+    return TRIS_OK;
+}
+
+int tris_stem_im2col_pair(const float* img, void* col, int n, int h, int w, tris_stream_t stream) {
+    if ((h & 1) || (w & 1) || (n & 1)) return tris::fail(TRIS_ERR_SHAPE, "tris_stem_im2col_pair: even n/h/w required");
+    stem_im2col_pair_kernel<<<grid1d(static_cast<long>(n) * (h / 2) * (w / 2)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        img, reinterpret_cast<__nv_bfloat16*>(col), n / 2, h, w);
+    TRIS_LAUNCH_OK("stem_im2col_pair_kernel");
+    return TRIS_OK;
+}
+
+int tris_pack_conv_blockdiag(const float* w, void* out, int co, int ci, int khw, int reps, tris_stream_t stream) {
+    pack_conv_blockdiag_kernel<<<grid1d(static_cast<long>(reps) * co * khw * reps * ci), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(out), co, ci, khw, reps);
+    TRIS_LAUNCH_OK("pack_conv_blockdiag_kernel");
+    return TRIS_OK;
+}
+
+int tris_unpack_conv_grad_blockdiag(const float* gp, float* gw, int co, int ci, int khw, int reps, tris_stream_t stream) {
+    unpack_conv_grad_blockdiag_kernel<<<grid1d(static_cast<long>(co) * ci * khw), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        gp, gw, co, ci, khw, reps);
+    TRIS_LAUNCH_OK("unpack_conv_grad_blockdiag_kernel");
+    return TRIS_OK;
+}
+
+int tris_fold_pairs(float* a, float* b, float* c, int half, tris_stream_t stream) {
+    fold_pairs_kernel<<<(half + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, c, half);
+    TRIS_LAUNCH_OK("fold_pairs_kernel");
     return TRIS_OK;
 }
 

@@ -47,7 +47,7 @@ def bn_apply(y, stats, bn: BNState, train, relu=True, pool=1, y1=None, stats1=No
     return out
 
 
-def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False):
+def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False, fold_half=0):
     """Returns (dy, dy1|None, g|None); accumulates dgamma/dbeta into bn.dgamma/bn.dbeta (fp32, pre-zeroed)."""
     n, h, w, c = y.shape
     dy = torch.empty_like(y)
@@ -57,7 +57,7 @@ def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState =
            _vp(bn.dgamma), _vp(bn.dbeta), _vp(dy), _vp(y1), _vp(bn1.gamma if bn1 else None),
            _vp(bn1.beta if bn1 else None), _vp(bn1.mean if bn1 else None), _vp(bn1.invstd if bn1 else None),
            _vp(bn1.dgamma if bn1 else None), _vp(bn1.dbeta if bn1 else None), _vp(dy1), _vp(g), n, h, w, c, pool,
-           int(relu), launches=2)
+           int(relu), int(fold_half), launches=2 + (1 if fold_half else 0))
     return dy, dy1, g
 
 
@@ -148,6 +148,28 @@ def stem_im2col(img):
     col = torch.empty((n * (h // 2) * (w // 2), 64), device=img.device, dtype=bf16)
     L.call("tris_stem_im2col", _vp(img), _vp(col), n, h, w)
     return col
+
+
+def stem_im2col_pair(img):
+    """img fp32 [N,3,H,W], N even -> col bf16 [(N/2)*(H/2)*(W/2), 64]: two images per row (columns 0..26 | 32..58)."""
+    n, _, h, w = img.shape
+    col = torch.empty(((n // 2) * (h // 2) * (w // 2), 64), device=img.device, dtype=bf16)
+    L.call("tris_stem_im2col_pair", _vp(img), _vp(col), n, h, w)
+    return col
+
+
+def pack_conv_blockdiag(w, out, reps=2):
+    co, ci, kh, kw = w.shape
+    L.call("tris_pack_conv_blockdiag", _vp(w), _vp(out), co, ci, kh * kw, reps)
+
+
+def unpack_conv_grad_blockdiag(gp, gw, reps=2):
+    co, ci, kh, kw = gw.shape
+    L.call("tris_unpack_conv_grad_blockdiag", _vp(gp), _vp(gw), co, ci, kh * kw, reps)
+
+
+def fold_pairs(a, b=None, c=None, half=32):
+    L.call("tris_fold_pairs", _vp(a), _vp(b), _vp(c), half)
 
 
 def f32_to_bf16(src, dst):

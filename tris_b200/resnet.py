@@ -9,6 +9,7 @@ BatchNorm batch statistics come out of the GEMM epilogues; BN-apply/ReLU/pool/re
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import torch
@@ -18,6 +19,7 @@ from . import ops
 from .ops import BNState
 
 bf16, f32 = torch.bfloat16, torch.float32
+PAIR_STEM = os.environ.get("TRIS_STEM_PAIR", "1") != "0"   # image-pair-packed stem for even batches
 
 
 class _Block:
@@ -59,12 +61,21 @@ class ResNetTower:
             st = BNState(z(), z(), z(), torch.ones(64, device=dev, dtype=f32), z(), z())
             self.pad_bn[prefix + nm] = st
         self.real_small_bn = {prefix + nm: real_bn(prefix + nm) for nm in ("bn1", "bn2")}
+        # image-pair-packed stem (even batches): channels [c | c + C] of a packed row are channel c of images 2i / 2i+1
+        self.pair_bn: Dict[str, BNState] = {}
+        for nm, cc in (("bn1", 32), ("bn2", 32), ("bn3", 64)):
+            z = lambda: torch.zeros(2 * cc, device=dev, dtype=f32)
+            self.pair_bn[prefix + nm] = BNState(z(), z(), z(), torch.ones(2 * cc, device=dev, dtype=f32), z(), z())
+        self.pair_real = {prefix + nm: real_bn(prefix + nm) for nm in ("bn1", "bn2", "bn3")}
+        self.w_pair1 = torch.zeros((64, 64), device=dev, dtype=bf16)
+        self.w_pair2 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
+        self.w_pair3 = torch.zeros((128, 9 * 64), device=dev, dtype=bf16)
         # ---- packed weights
         self.w_stem1 = torch.zeros((64, 64), device=dev, dtype=bf16)
         self.w_stem2 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
         self.w_stem3 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
         self.w3x3 = {blk.p: torch.empty((blk.planes, 9 * blk.planes), device=dev, dtype=bf16) for blk in self.blocks}
-        n_stats = 2 * (64 * 3 + sum(b.planes * 2 + b.planes * 4 * (2 if b.down else 1) for b in self.blocks))
+        n_stats = 2 * (64 * 2 + 128 + sum(b.planes * 2 + b.planes * 4 * (2 if b.down else 1) for b in self.blocks))
         self.stats_buf = torch.zeros(n_stats, device=dev, dtype=f32)
         self.bn_keys = [k for k, _ in module.named_buffers() if k.startswith(prefix) and k.endswith("num_batches_tracked")
                         and "attnpool" not in k]
@@ -84,6 +95,14 @@ class ResNetTower:
             real = self.real_small_bn[k]
             pad.gamma[:32].copy_(real.gamma); pad.beta[:32].copy_(real.beta)
             pad.rm[:32].copy_(real.rm); pad.rv[:32].copy_(real.rv)
+        self.w_pair1[:32, :27].copy_(self._tmp27())
+        self.w_pair1[32:, 32:59].copy_(self._tmp27())
+        ops.pack_conv_blockdiag(st.p(p + "conv2.weight"), self.w_pair2)
+        ops.pack_conv_blockdiag(st.p(p + "conv3.weight"), self.w_pair3)
+        for k, pr in self.pair_bn.items():
+            real, c = self.pair_real[k], self.pair_real[k].gamma.numel()
+            for dst, src in ((pr.gamma, real.gamma), (pr.beta, real.beta), (pr.rm, real.rm), (pr.rv, real.rv)):
+                dst[:c].copy_(src); dst[c:].copy_(src)
 
     def _tmp27(self):
         if not hasattr(self, "_t27"):
@@ -111,6 +130,39 @@ class ResNetTower:
             so[0] += 2 * c
             return s
 
+        pair = PAIR_STEM and B % 2 == 0
+        if pair:
+            x, stem_rec = self._stem_fwd_pair(img, train, stats)
+        else:
+            x, stem_rec = self._stem_fwd_padded(img, train, stats)
+        if train:
+            tape["stem"] = (pair,) + stem_rec
+        feats = []
+        for blk in self.blocks:
+            x, rec = self._block_fwd(blk, x, train, stats)
+            if train:
+                tape[blk.p] = rec
+        if train:
+            torch._foreach_add_(self.nbt, 1)
+            self._sync_private_running_stats()
+        return x, tape
+
+    def _sync_private_running_stats(self):
+        """The stem BatchNorms run on private padded / pair-packed copies of their parameters; after a train-mode forward
+        the real running statistics (already updated) are mirrored into BOTH sets so that either stem path can follow."""
+        p = self.prefix
+        for nm in ("bn1", "bn2"):
+            pad, real = self.pad_bn[p + nm], self.real_small_bn[p + nm]
+            pad.rm[:32].copy_(real.rm); pad.rv[:32].copy_(real.rv)
+        for nm in ("bn1", "bn2", "bn3"):
+            pr, real = self.pair_bn[p + nm], self.pair_real[p + nm]
+            c = real.rm.numel()
+            pr.rm[:c].copy_(real.rm); pr.rm[c:].copy_(real.rm); pr.rv[:c].copy_(real.rv); pr.rv[c:].copy_(real.rv)
+
+    def _stem_fwd_padded(self, img, train, stats):
+        """Odd batches: the two 32-channel activations are carried zero-padded to 64 channels."""
+        p = self.prefix
+        B, _, H, W = img.shape
         col = ops.stem_im2col(img.contiguous())
         s = stats(64)
         y1 = G.linear_fwd(col, self.w_stem1, stats=s).view(B, H // 2, W // 2, 64)
@@ -122,18 +174,42 @@ class ResNetTower:
         y3 = G.conv3x3_fwd(a2, self.w_stem3, stats=s3)
         x = ops.bn_apply(y3, s3, self.bn[p + "bn3"], train, pool=2)
         if train:
-            tape["stem"] = (col, y1, a1, y2, a2, y3)
             for nm in ("bn1", "bn2"):   # running stats of the padded copies back into the real buffers
                 pad, real = self.pad_bn[p + nm], self.real_small_bn[p + nm]
                 real.rm.copy_(pad.rm[:32]); real.rv.copy_(pad.rv[:32])
-        feats = []
-        for blk in self.blocks:
-            x, rec = self._block_fwd(blk, x, train, stats)
-            if train:
-                tape[blk.p] = rec
+        return x, (col, y1, a1, y2, a2, y3)
+
+    def _stem_fwd_pair(self, img, train, stats):
+        """Even batches: images (2i, 2i+1) share one row -- [B/2, h, w, 2*C] with block-diagonal weights.  The 32-channel
+        tensors are then dense 64-channel rows (half the pixels of the padded form: half the MMA work for conv1 / conv2,
+        half the BatchNorm traffic) and conv3 becomes a full 128-wide tile.  Channels c and c + C are one BatchNorm channel:
+        their batch sums are folded (averaged, so that sum / (pixels of B/2 images) is the full-batch mean)."""
+        p = self.prefix
+        B, _, H, W = img.shape
+        B2 = B // 2
+        col = ops.stem_im2col_pair(img.contiguous())
+        s = stats(64)
+        y1 = G.linear_fwd(col, self.w_pair1, stats=s).view(B2, H // 2, W // 2, 64)
         if train:
-            torch._foreach_add_(self.nbt, 1)
-        return x, tape
+            ops.fold_pairs(s[:64], s[64:], half=32)
+        a1 = ops.bn_apply(y1, s, self.pair_bn[p + "bn1"], train)
+        s2 = stats(64)
+        y2 = G.conv3x3_fwd(a1, self.w_pair2, stats=s2)
+        if train:
+            ops.fold_pairs(s2[:64], s2[64:], half=32)
+        a2 = ops.bn_apply(y2, s2, self.pair_bn[p + "bn2"], train)
+        s3 = stats(128)
+        y3 = G.conv3x3_fwd(a2, self.w_pair3, stats=s3)
+        if train:
+            ops.fold_pairs(s3[:128], s3[128:], half=64)
+        xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2)                  # [B/2, H/4, W/4, 128]
+        x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64)   # un-pair: layout only
+        if train:
+            for nm in ("bn1", "bn2", "bn3"):
+                pr, real = self.pair_bn[p + nm], self.pair_real[p + nm]
+                c = real.rm.numel()
+                real.rm.copy_(pr.rm[:c]); real.rv.copy_(pr.rv[:c])
+        return x, (col, y1, a1, y2, a2, y3)
 
     def _block_fwd(self, blk: _Block, x, train, stats):
         B, H, W, Cin = x.shape
@@ -205,7 +281,13 @@ class ResNetTower:
         st, p = self.store, self.prefix
         for blk in reversed(self.blocks):
             dout = self._block_bwd(blk, tape[blk.p], dout)
-        col, y1, a1, y2, a2, y3 = tape["stem"]
+        self._stem_bwd(tape["stem"], dout)
+
+    def _stem_bwd(self, stem_rec, dout):
+        st, p = self.store, self.prefix
+        pair, col, y1, a1, y2, a2, y3 = stem_rec
+        if pair:
+            return self._stem_bwd_pair(dout, col, y1, a1, y2, a2, y3)
         dy3, _, _ = ops.bn_bwd(dout, None, y3, self.bn[p + "bn3"], pool=2)
         self._wgrad3x3(dy3, a2, p + "conv3.weight", ci_pad=64)
         da2 = G.conv3x3_dgrad(dy3, self.w_stem3, 64)
@@ -217,6 +299,7 @@ class ResNetTower:
         pb1 = self.pad_bn[p + "bn1"]
         pb1.dgamma.zero_(); pb1.dbeta.zero_()
         dy1, _, _ = ops.bn_bwd(da1, None, y1, pb1)
+
         def stem1():
             gw = G.linear_wgrad(dy1.view(-1, 64), col)                   # [64, 64] fp32
             g1 = st.g(p + "conv1.weight")                                # [32,3,3,3]
@@ -225,6 +308,41 @@ class ResNetTower:
         for nm, pad in (("bn1", pb1), ("bn2", pb2)):
             st.g(p + nm + ".weight").add_(pad.dgamma[:32])
             st.g(p + nm + ".bias").add_(pad.dbeta[:32])
+
+    def _stem_bwd_pair(self, dout, col, y1, a1, y2, a2, y3):
+        st, p = self.store, self.prefix
+        B, h4, w4, _ = dout.shape
+        B2 = B // 2
+        for nm in ("bn1", "bn2", "bn3"):
+            pr = self.pair_bn[p + nm]
+            pr.dgamma.zero_(); pr.dbeta.zero_()
+        dxp = dout.view(B2, 2, h4, w4, 64).permute(0, 2, 3, 1, 4).reshape(B2, h4, w4, 128)             # re-pair: layout only
+        dy3, _, _ = ops.bn_bwd(dxp, None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64)
+        self._wgrad3x3_pair(dy3, a2, p + "conv3.weight")
+        da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64)
+        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.pair_bn[p + "bn2"], fold_half=32)
+        self._wgrad3x3_pair(dy2, a1, p + "conv2.weight")
+        da1 = G.conv3x3_dgrad(dy2, self.w_pair2, 64)
+        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.pair_bn[p + "bn1"], fold_half=32)
+
+        def stem1():
+            gw = G.linear_wgrad(dy1.view(-1, 64), col)                   # [64, 64] fp32, two diagonal 32 x 27 blocks
+            g1 = st.g(p + "conv1.weight")
+            g1.add_((gw[:32, :27] + gw[32:, 32:59]).reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+        self._wg(stem1, dy1, col)
+        for nm in ("bn1", "bn2", "bn3"):     # folded sums hold the pair AVERAGE: the full-batch gradient is twice that
+            pr = self.pair_bn[p + nm]
+            c = pr.dgamma.numel() // 2
+            st.g(p + nm + ".weight").add_(pr.dgamma[:c], alpha=2.0)
+            st.g(p + nm + ".bias").add_(pr.dbeta[:c], alpha=2.0)
+
+    def _wgrad3x3_pair(self, dy, x, key):
+        gw = self.store.g(key)
+
+        def run():
+            gp = G.conv3x3_wgrad(dy, x)
+            ops.unpack_conv_grad_blockdiag(gp, gw, 2)
+        self._wg(run, dy, x)
 
     def _wgrad3x3(self, dy, x, key, ci_pad=None):
         gw = self.store.g(key)
