@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
 
 // InstanceNorm over the P pixels of each image, per channel.  x bf16 [B*P, ldx] (channel offset applied by caller),
 // block = (64 channels, 4 pixel groups), grid = (C/64, B).   out = mix_scale * (IN(x)*gamma+beta [relu]) + mix_add
-constexpr int IN_MAXP = 32;   // per-thread pixels (P <= 4*IN_MAXP)
+// per-thread pixel cache IN_MAXP: P <= 4 * IN_MAXP (32 -> 128 pixels = 320x320 inputs; 64 -> 256 pixels = up to 512x512)
+template <int IN_MAXP>
 __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const __nv_bfloat16* __restrict__ mix_add,
                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out,
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const __nv_bfloat16* 
 }
 
 // backward of out = mix_scale * act(IN(x)*gamma+beta): dx, dgamma/dbeta (atomics).  relu mask recomputed from x.
+template <int IN_MAXP>
 __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
@@ -430,8 +432,9 @@ int tris_l2norm_bwd(const void* dy, const void* y, const float* inv_norm, void* 
 
 int tris_instnorm_fwd(const void* x, const float* gamma, const float* beta, const void* mix_add, void* out, float* mean,
                       float* invstd, int batch, int P, int C, float mix_scale, int relu, float eps, tris_stream_t stream) {
-    if (C % 64 || P > 4 * IN_MAXP) return tris::fail(TRIS_ERR_SHAPE, "tris_instnorm_fwd: C%%64, P<=%d", 4 * IN_MAXP);
-    instnorm_fwd_kernel<<<dim3(C / 64, batch), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    if (C % 64 || P > 256) return tris::fail(TRIS_ERR_SHAPE, "tris_instnorm_fwd: C%%64, P<=256 (got C=%d P=%d)", C, P);
+    auto fn = P <= 128 ? instnorm_fwd_kernel<32> : instnorm_fwd_kernel<64>;
+    fn<<<dim3(C / 64, batch), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<const __nv_bfloat16*>(mix_add),
         reinterpret_cast<__nv_bfloat16*>(out), mean, invstd, P, C, mix_scale, relu, eps);
     TRIS_LAUNCH_OK("instnorm_fwd_kernel");
@@ -441,8 +444,9 @@ int tris_instnorm_fwd(const void* x, const float* gamma, const float* beta, cons
 int tris_instnorm_bwd(const void* dout, const void* x, const float* gamma, const float* beta, const float* mean,
                       const float* invstd, void* dx, float* dgamma, float* dbeta, int batch, int P, int C, float mix_scale,
                       int relu, tris_stream_t stream) {
-    if (C % 64 || P > 4 * IN_MAXP) return tris::fail(TRIS_ERR_SHAPE, "tris_instnorm_bwd: C%%64, P<=%d", 4 * IN_MAXP);
-    instnorm_bwd_kernel<<<dim3(C / 64, batch), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    if (C % 64 || P > 256) return tris::fail(TRIS_ERR_SHAPE, "tris_instnorm_bwd: C%%64, P<=256 (got C=%d P=%d)", C, P);
+    auto fn = P <= 128 ? instnorm_bwd_kernel<32> : instnorm_bwd_kernel<64>;
+    fn<<<dim3(C / 64, batch), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, mean, invstd,
         reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, P, C, mix_scale, relu);
     TRIS_LAUNCH_OK("instnorm_bwd_kernel");

@@ -13,9 +13,13 @@ from . import _lib as L
 SMS = 148
 
 
+# measured cost of one 64-deep k-block of a 128 x BN tile on one SM (us): the L2 -> smem feed ((128 + BN) * 128 B at ~120 GB/s
+# per SM) for narrow tiles, the MMA itself (128 * BN * 64 MACs at 9.4 TFLOP/s per SM) for BN = 256 (tools/gemm_trace.py)
+_KBLOCK_US = {32: 0.17, 64: 0.20, 128: 0.27, 256: 0.45}
+
+
 def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
-    """UMMA N per tile.  The mainloop is L2->smem bound for narrow tiles (a 128 x BN tile moves (128 + BN) * 128 B per
-    k-block for BN * 128 * 64 MACs), so pick the width that minimises  waves(148 SMs) * (128 + BN)."""
+    """UMMA N per tile: the width that minimises  waves(148 SMs) x (time of one k-block at that width)."""
     if n <= 32 and not mn_major_b:
         return 32
     n_pad = ((n + 63) // 64) * 64
@@ -25,8 +29,8 @@ def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
             continue
         tiles = tiles_m * ((n + bn - 1) // bn)
         waves = (tiles + SMS - 1) // SMS
-        cost = waves * (128 + bn)
-        if best_cost is None or cost <= best_cost:
+        cost = waves * _KBLOCK_US[bn]
+        if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best
 

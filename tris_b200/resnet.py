@@ -203,7 +203,7 @@ class ResNetTower:
         if train:
             ops.fold_pairs(s3[:128], s3[128:], half=64)
         xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2)                  # [B/2, H/4, W/4, 128]
-        x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64)   # un-pair: layout only
+        x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64).contiguous()   # un-pair: layout only
         if train:
             for nm in ("bn1", "bn2", "bn3"):
                 pr, real = self.pair_bn[p + nm], self.pair_real[p + nm]
@@ -316,7 +316,7 @@ class ResNetTower:
         for nm in ("bn1", "bn2", "bn3"):
             pr = self.pair_bn[p + nm]
             pr.dgamma.zero_(); pr.dbeta.zero_()
-        dxp = dout.view(B2, 2, h4, w4, 64).permute(0, 2, 3, 1, 4).reshape(B2, h4, w4, 128)             # re-pair: layout only
+        dxp = dout.reshape(B2, 2, h4, w4, 64).permute(0, 2, 3, 1, 4).reshape(B2, h4, w4, 128).contiguous()   # re-pair: layout only
         dy3, _, _ = ops.bn_bwd(dxp, None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64)
         self._wgrad3x3_pair(dy3, a2, p + "conv3.weight")
         da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64)
