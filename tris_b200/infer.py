@@ -1,0 +1,76 @@
+"""CUDA-graph wrappers for the batch-1 inference drivers (validate.py / demo.py): at batch 1 the eval forward is a chain of
+~350 small launches (RN50 ~110, text tower ~100, head ~25, aux ViT ~110), i.e. launch-latency bound in eager mode; with
+static shapes each phase is captured once and replayed per ref."""
+from __future__ import annotations
+
+import torch
+
+
+class GraphRunner:
+    """Capture ``fn(*static_inputs)`` once; calls copy new inputs into the static buffers and replay.  The returned
+    tensors are the graph's static outputs: consume them before the next call."""
+
+    def __init__(self, fn, *example_inputs):
+        self.static_in = [t.clone() for t in example_inputs]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                fn(*self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for s, t in zip(self.static_in, inputs):
+            s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+class Stage1Inference:
+    """image features once per ref + one response map per sentence (+ PRMS scoring), graph-replayed."""
+
+    def __init__(self, model, aux=None, use_graphs=True):
+        self.model, self.aux, self.use_graphs = model.eval(), aux, use_graphs
+        self._feat = self._resp = None
+        self._score = {}
+
+    def features(self, img):
+        if not self.use_graphs:
+            return self.model.image_features(img)
+        if self._feat is None or self._feat.static_in[0].shape != img.shape:
+            self.model.engine().ensure_fresh()
+            self._feat = GraphRunner(self.model.image_features, img)
+        return self._feat(img)
+
+    def respond(self, c4, ids, img_size):
+        if not self.use_graphs:
+            return self.model.respond(c4, ids, img_size)
+        if self._resp is None or self._resp.static_in[1].shape != ids.shape or self._resp.static_in[0].shape != c4.shape:
+            self._resp = GraphRunner(lambda c, i: self.model.respond(c, i, img_size), c4, ids)
+        return self._resp(c4, ids)
+
+    def prms_scores(self, cams, img, ids):
+        """[S, S] cosine scores of fg_j = cam_j * img (224 x 224) against every sentence of the ref (validate.py:304-332)."""
+        from . import ops
+        eng = self.aux._engine()
+        S = ids.shape[0]
+
+        def run(cams_, img_, ids_):
+            patches, _ = ops.mask_resize_fwd(cams_, img_.float().expand(S, -1, -1, -1).contiguous(), 224, 32)
+            return eng.encode_patches(patches, S), eng.encode_text_hidden(ids_)
+        if not self.use_graphs:
+            f, g = run(cams, img, ids)
+        else:
+            if S not in self._score:
+                eng.ensure_fresh()
+                self._score[S] = GraphRunner(run, cams, img, ids)
+            f, g = self._score[S](cams, img, ids)
+        f, g = f.float(), g.float()
+        f = f / f.norm(dim=-1, keepdim=True)
+        g = g / g.norm(dim=-1, keepdim=True)
+        return f @ g.t()

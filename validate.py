@@ -57,13 +57,14 @@ def _iou_hit(cam, target):
 
 @torch.no_grad()
 def validate(args, refs, model, local_rank=0):
-    model.eval()
+    from tris_b200.infer import Stage1Inference
+    inf = Stage1Inference(model, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
     ious, hits = [], []
     for idx, img, word_ids, target in refs:
         img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
-        c4 = model.image_features(img)                          # once per ref
+        c4 = inf.features(img)                                  # once per ref
         for j in range(word_ids.shape[-1]):
-            out = model.respond(c4, word_ids[:, :, j].contiguous(), img.shape[2:])
+            out = inf.respond(c4, word_ids[:, :, j].contiguous(), tuple(img.shape[2:]))
             cam = _to_original(out, target.shape[-2:])[0, 0]
             iou, hit, cam = _iou_hit(cam, target[0])
             ious.append(iou)
@@ -77,22 +78,16 @@ def validate(args, refs, model, local_rank=0):
 @torch.no_grad()
 def validate_same_sentence(args, refs, model, aux, local_rank=0):
     """PRMS map selection (validate.py:253-387) with per-ref de-duplicated encoders."""
-    from tris_b200 import ops
-    model.eval()
-    eng = aux._engine()
+    from tris_b200.infer import Stage1Inference
+    inf = Stage1Inference(model, aux, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
     ious, names = [], []
     for idx, img, word_ids, target in refs:
         img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
         S = word_ids.shape[-1]
         ids = word_ids[0].t().contiguous()                                     # [S, L]
-        c4 = model.image_features(img)
-        cams = torch.cat([model.respond(c4, ids[j:j + 1], img.shape[2:]) for j in range(S)])       # [S,1,H,W]
-        patches, _ = ops.mask_resize_fwd(cams, img.float().expand(S, -1, -1, -1).contiguous(), 224, 32)   # fg_j = cam_j * img
-        f = eng.encode_patches(patches, S).float()
-        g = eng.encode_text_hidden(ids).float()
-        f = f / f.norm(dim=-1, keepdim=True)
-        g = g / g.norm(dim=-1, keepdim=True)
-        best = int((f @ g.t()).sum(dim=1).argmax())                              # get_scores summed over the ref's sentences
+        c4 = inf.features(img)
+        cams = torch.cat([inf.respond(c4, ids[j:j + 1], tuple(img.shape[2:])).clone() for j in range(S)])   # [S,1,H,W]
+        best = int(inf.prms_scores(cams, img, ids).sum(dim=1).argmax())         # get_scores summed over the ref's sentences
         cam = _to_original(cams[best:best + 1], target.shape[-2:])[0, 0]
         iou, _, cam = _iou_hit(cam, target[0])
         ious.append(iou)
