@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/probe.txt 2>&1; nproc >> gpurun_out/probe.txt
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -30 > gpurun_out/pytest_gpu.txt
 cat gpurun_out/pytest_gpu.txt | tail -8
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" != "quick" ]; then
@@ -14,6 +15,7 @@ timeout 120 python demo.py --synthetic --output gpurun_out/demo_cam.npy > gpurun
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches.csv gpurun_out/gemm_traffic.json > gpurun_out/launch_summary.txt 2>&1
 head -30 gpurun_out/launch_summary.txt
+python tools/profile_sections.py 48 > gpurun_out/sections.txt 2>&1; cat gpurun_out/sections.txt
 rm -f gpurun_out/prof_targets.ncu-rep
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_targets python tools/ncu_targets.py > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log

@@ -6,6 +6,8 @@ with k = (r*3+s)*Cin + ci  (``pack_conv3x3``).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -33,6 +35,9 @@ def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best
+
+
+WGRAD_MAX_CTAS = int(os.environ.get("TRIS_WGRAD_CTAS", "0"))   # experiment: cap the SMs a side-stream weight gradient takes
 
 
 def _desc(**kw) -> L.GemmDesc:
@@ -120,7 +125,7 @@ def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
         out.zero_()
     _chk(out, torch.float32, "out")
     d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, M=n, N=k, K=m, lda=n, ldb=k,
-              ldd=k, taps=1, block_n=bn, split_k=sk, out_dtype=L.DT_F32, atomic=atomic)
+              ldd=k, taps=1, block_n=bn, split_k=sk, out_dtype=L.DT_F32, atomic=atomic, max_ctas=WGRAD_MAX_CTAS)
     L.gemm_raw(d)
     return out
 
@@ -206,7 +211,7 @@ def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
         out.zero_()
     d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_CONV, M=co, N=ci, K=n * h * w,
               ldd=9 * ci, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, wgrad=1, block_n=bn, split_k=sk,
-              out_dtype=L.DT_F32, atomic=atomic)
+              out_dtype=L.DT_F32, atomic=atomic, max_ctas=WGRAD_MAX_CTAS)
     L.gemm_raw(d)
     return out
 
