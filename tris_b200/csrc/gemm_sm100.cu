@@ -421,6 +421,28 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->acc_empty[buf]));
             ptx::fence_proxy_async_smem();
             ptx::named_bar_sync(1, 256);
+            // ---- TMA store (one elected thread), issued BEFORE the statistics pass: both only read the staged tile, so the
+            // store drains while the epilogue warps accumulate the column sums
+            if (tid_e == 0 && !(p.dbg & 4)) {
+                for (int g = 0; g < ngroups; ++g) {
+                    const int cg = n0 + g * gw;
+                    if (cg >= p.N) break;
+                    const uint32_t src = stg + g * 16384;
+                    if (AM == LD_CONV) {
+                        ptx::tma_store_4d(&map_d, src, cg, c.w0, c.h0, c.n_i);
+                    } else if (p.wgrad) {
+                        ptx::tma_reduce_add_3d(&map_d, src, cg, c.tap, c.m_t * kBlockM);
+                    } else if (p.batch > 1) {
+                        if (p.atomic) ptx::tma_reduce_add_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
+                        else ptx::tma_store_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
+                    } else if (p.atomic) {
+                        ptx::tma_reduce_add_2d(&map_d, src, cg, c.m_t * kBlockM);
+                    } else {
+                        ptx::tma_store_2d(&map_d, src, cg, c.m_t * kBlockM);
+                    }
+                }
+                ptx::bulk_commit();
+            }
             // ---- BatchNorm column statistics of the stored (bf16-rounded) tile.  Thread = (16-byte vector of 8 columns,
             // row part): one LDS.128 + 3 instructions per element; parts are combined through a 16 KB scratch and the
             // per-CTA totals live in smem until the kernel ends (one global atomic per column per CTA).
@@ -467,27 +489,6 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
             }
             if ((p.dbg & 8) && blockIdx.x == 0 && tid_e == 0 && it < 64) p.dbg_buf[6 * 64 + it] = clock64();
-            // ---- TMA store (one elected thread)
-            if (tid_e == 0 && !(p.dbg & 4)) {
-                for (int g = 0; g < ngroups; ++g) {
-                    const int cg = n0 + g * gw;
-                    if (cg >= p.N) break;
-                    const uint32_t src = stg + g * 16384;
-                    if (AM == LD_CONV) {
-                        ptx::tma_store_4d(&map_d, src, cg, c.w0, c.h0, c.n_i);
-                    } else if (p.wgrad) {
-                        ptx::tma_reduce_add_3d(&map_d, src, cg, c.tap, c.m_t * kBlockM);
-                    } else if (p.batch > 1) {
-                        if (p.atomic) ptx::tma_reduce_add_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
-                        else ptx::tma_store_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
-                    } else if (p.atomic) {
-                        ptx::tma_reduce_add_2d(&map_d, src, cg, c.m_t * kBlockM);
-                    } else {
-                        ptx::tma_store_2d(&map_d, src, cg, c.m_t * kBlockM);
-                    }
-                }
-                ptx::bulk_commit();
-            }
         }
         if (tid_e == 0) ptx::bulk_wait_all();
         if (p.stats != nullptr) {
