@@ -19,6 +19,8 @@ LIB = os.path.join(LIBDIR, "libtris_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+if os.environ.get("TRIS_GEMM_MAXNREG"):      # experiment knob: cap the GEMM kernel's registers (co-residency with BN kernels)
+    FLAGS.append("-DTRIS_GEMM_MAXNREG=" + os.environ["TRIS_GEMM_MAXNREG"])
 
 
 def _sources():

@@ -120,7 +120,12 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4 };
 
 template <int AM, int BM>
-__global__ void __launch_bounds__(kThreads, 1)
+// 96 registers/thread (no spills; 166 unconstrained): 352 x 96 = 33 K registers leave room for one 256-thread CTA of the
+// HBM-bound BatchNorm kernels next to a resident GEMM CTA, so side-stream weight gradients and the BN chain share SMs.
+#ifndef TRIS_GEMM_MAXNREG
+#define TRIS_GEMM_MAXNREG 96
+#endif
+__global__ void __maxnreg__(TRIS_GEMM_MAXNREG)
 tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_d, const KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
