@@ -262,7 +262,10 @@ def run_gpu_arm(a):
         # reaches them: the per-launch event pairs then measure kernel durations rather than Python launch gaps
         how = "CUDA-event pair per launch, eager fwd+bwd queued behind a 100 ms spin kernel, side-stream overlap off"
         torch.cuda.synchronize()
-        torch.cuda._sleep(int(2.0e8))
+        try:
+            torch.cuda._sleep(int(2.0e8))
+        except Exception:  # pragma: no cover  (private helper; without it the figure only gets more conservative)
+            how = "CUDA-event pair per launch, eager fwd+bwd, side-stream overlap off"
         trainer._fwd_bwd(*dev[0])
         torch.cuda.synchronize()
         t_ms = sum(c[0].elapsed_time(c[1]) for c in gemm_calls)

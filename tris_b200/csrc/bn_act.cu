@@ -6,6 +6,8 @@
 // Batch statistics (sum, sum of squares) arrive from the conv GEMM epilogue (gemm_sm100.cu).
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace {
@@ -375,7 +377,9 @@ __global__ void __launch_bounds__(kThreads) avgpool2_bwd_kernel(const __nv_bfloa
 
 int grid_for(long total_threads) {
     long blocks = (total_threads + kThreads - 1) / kThreads;
-    const long cap = static_cast<long>(tris::sm_count()) * 8;   // 8 resident CTAs of 256 threads per SM
+    static int per_sm = 0;   // TRIS_BN_CTAS: CTAs per SM of the streaming kernels (experiment knob; default 8)
+    if (per_sm == 0) { const char* e = getenv("TRIS_BN_CTAS"); per_sm = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 8; }
+    const long cap = static_cast<long>(tris::sm_count()) * per_sm;
     return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 namespace tris {
 
@@ -77,6 +78,18 @@ const CUtensorMap* tensor_map_bf16(const void* base, int rank, const uint64_t* d
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
+    // The key contains the base pointer, so an eager caller whose allocations keep moving would grow the cache without
+    // bound: past 32 K entries start over (descriptors are passed to kernels BY VALUE at launch, so none is in use here;
+    // the old maps are kept alive in a graveyard because callers may still hold the returned pointer for this launch).
+    static std::vector<CUtensorMap*> graveyard;
+    if (cache.size() > 32768) {
+        for (auto& kv : cache) graveyard.push_back(kv.second);
+        cache.clear();
+        if (graveyard.size() > 4 * 32768) {
+            for (size_t i = 0; i + 32768 < graveyard.size(); ++i) delete graveyard[i];
+            graveyard.erase(graveyard.begin(), graveyard.end() - 32768);
+        }
+    }
     auto fn = encode_fn();
     if (!fn) {
         fail(TRIS_ERR_ARCH, "cuTensorMapEncodeTiled not available from the driver");

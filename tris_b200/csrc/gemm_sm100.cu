@@ -613,10 +613,12 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 + 16384 : 0;
     p.nacc = 512 / bn >= 4 ? 4 : 2;   // power of two (ring index = it & (nacc - 1))
     p.acc_stride = bn;
+    static uint32_t smem_cap = 0;   // TRIS_GEMM_SMEM_KB: leave shared memory for co-resident streaming kernels (experiment knob)
+    if (smem_cap == 0) { const char* e = getenv("TRIS_GEMM_SMEM_KB"); smem_cap = (e && atoi(e) >= 64 && atoi(e) <= 227) ? atoi(e) * 1024u : 227u * 1024u; }
     const uint32_t fixed = 1024 + sizeof(SmemCtl) + 64 + p.stats_bytes;
     // two staging buffers (store of tile i overlaps the epilogue of tile i+1) when >= 4 pipeline stages still fit
-    p.nstg = (227 * 1024 - fixed - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
-    const uint32_t budget = 227 * 1024 - fixed - p.nstg * p.staging_bytes;
+    p.nstg = (smem_cap - fixed - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
+    const uint32_t budget = smem_cap - fixed - p.nstg * p.staging_bytes;
     p.stages = budget / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     { const char* e = getenv("TRIS_GEMM_STAGES"); if (e && atoi(e) >= 2 && (uint32_t)atoi(e) < p.stages) p.stages = atoi(e); }
