@@ -147,6 +147,8 @@ int tris_resize_bilinear_ac(const float* src, float* dst, long nc, int H, int W,
 /* fg loss (clip_forward + MaxLoss, train_stage1.py:263-284,340), negative loss (:342-353), multilabel soft margin (:354), weighted sum (:364). */
 int tris_stage1_loss_fwd(const void* f, const void* g, const float* cls, float* out, int B, int D, int K, float w1,
     float w4, float w5, tris_stream_t stream);
+int tris_stage1_loss_fwd_f32(const float* f, const float* g, const float* cls, float* out, int B, int D, int K, float w1, float w4,
+    float w5, tris_stream_t stream);
 /* gradients of the weighted sum w.r.t. the image features and cls_out. */
 int tris_stage1_loss_bwd(const void* f, const void* g, const float* cls, const float* dout, void* df, float* dcls,
     int B, int D, int K, float w1, float w4, float w5, tris_stream_t stream);
@@ -240,6 +242,7 @@ int tris_embed_f32(const int* ids, const float* E, const float* P, float* x, int
 int tris_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int D, float eps,
     tris_stream_t stream);
 int tris_attn_f32(const float* qkv, float* out, int n, int L, int heads, int causal, tris_stream_t stream);
+int tris_vit_assemble_f32(const float* patch, const float* cls, const float* pos, float* tok, int n, int T, int D, tris_stream_t stream);
 int tris_gather_rows_f32(const float* x, const int* idx, float* out, int rows, int D, tris_stream_t stream);
 int tris_l2norm_f32(const float* x, float* y, int rows, int D, tris_stream_t stream);
 int tris_instnorm_f32(const float* x, const float* gamma, const float* beta, const float* mix_add, float* out, int

@@ -65,3 +65,19 @@ def test_fp32_mode_is_forward_only(setup):
     with pytest.raises(ValueError):
         m.set_precision("fp16")
     m.set_precision("fp32")
+
+
+def test_fp32_step_losses_vs_reference(setup, golden):
+    """Forward of the WHOLE training step in fp32 (TRIS forward, mask-and-resize, frozen ViT-B/32 + text tower on positives
+    and negatives, the three losses) against the losses the unmodified reference produced (train_stage1.py:320-364)."""
+    from oracle import weights as W
+    from tris_b200 import clip_model
+    from tris_b200.precise import PreciseStage1
+    b, size, l, neg, sub, s_tris, s_aux, s_data = [int(v) for v in golden["meta"]]
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=l)
+    aux.load_state_dict(W.make_vitb32_clip_state_dict(s_aux, cos_bias=True), strict=True)
+    _, _, negs = W.synthetic_batch(b, size, l, neg, s_data)
+    m = setup["model"].train()
+    out = PreciseStage1(m).step_losses(aux, setup["img"], setup["ids"], negs.cuda()).cpu().numpy()
+    print("fp32 step losses", out, golden["losses"])
+    np.testing.assert_allclose(out, golden["losses"], rtol=1e-3)

@@ -505,13 +505,19 @@ __global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------ losses (K12)
 // f bf16 [B, D] image features, g bf16 [B*(1+K), D] text features (positives first, then negatives b-major),
 // cls f32 [B, B].   out[4] = {loss, l1, l4, l5}.   Single CTA, warp per sample: deterministic.
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+
+template <typename T>
 struct LossParams {
-    const __nv_bfloat16* f;
-    const __nv_bfloat16* g;
+    const T* f;
+    const T* g;
     const float* cls;
     float* out;
     const float* dout;          // backward: gradient w.r.t. out[4]
-    __nv_bfloat16* df;          // backward: [B, D]
+    T* df;                      // backward: [B, D]
     float* dcls;                // backward: [B, B]
     int B, D, K;
     float w1, w4, w5;
@@ -519,8 +525,8 @@ struct LossParams {
 
 __device__ __forceinline__ float softplus(float x) { return x > 15.f ? x : log1pf(__expf(x)); }
 
-template <bool kBackward>
-__global__ void __launch_bounds__(512) loss_kernel(const LossParams p) {
+template <bool kBackward, typename T>
+__global__ void __launch_bounds__(512) loss_kernel(const LossParams<T> p) {
     __shared__ float part[3][16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int B = p.B, D = p.D, K = p.K;
@@ -532,17 +538,17 @@ __global__ void __launch_bounds__(512) loss_kernel(const LossParams p) {
     }
     float l1 = 0.f, l4 = 0.f, l5 = 0.f;
     for (int b = warp; b < B; b += nw) {
-        const __nv_bfloat16* fr = p.f + static_cast<long>(b) * D;
+        const T* fr = p.f + static_cast<long>(b) * D;
         float ff = 0.f;
-        for (int i = lane; i < D; i += 32) { const float v = __bfloat162float(fr[i]); ff += v * v; }
+        for (int i = lane; i < D; i += 32) { const float v = ldf(fr + i); ff += v * v; }
         const float finv = rsqrtf(warp_sum(ff));
         // positive text
-        const __nv_bfloat16* gr = p.g + static_cast<long>(b) * D;
+        const T* gr = p.g + static_cast<long>(b) * D;
         float gg = 0.f, fg = 0.f;
         for (int i = lane; i < D; i += 32) {
-            const float gv = __bfloat162float(gr[i]);
+            const float gv = ldf(gr + i);
             gg += gv * gv;
-            fg += gv * __bfloat162float(fr[i]);
+            fg += gv * ldf(fr + i);
         }
         const float ginv = rsqrtf(warp_sum(gg));
         const float cosv = warp_sum(fg) * finv * ginv;
@@ -553,12 +559,12 @@ __global__ void __launch_bounds__(512) loss_kernel(const LossParams p) {
         if (kBackward && cosv > 1e-4f && cosv < 0.9999f) coef_pos = -c1 / (B * cosv);
         float coef_neg[8], ninv[8];
         for (int k = 0; k < K; ++k) {
-            const __nv_bfloat16* nr = p.g + (static_cast<long>(B) + static_cast<long>(b) * K + k) * D;
+            const T* nr = p.g + (static_cast<long>(B) + static_cast<long>(b) * K + k) * D;
             float nn = 0.f, fn = 0.f;
             for (int i = lane; i < D; i += 32) {
-                const float nv = __bfloat162float(nr[i]);
+                const float nv = ldf(nr + i);
                 nn += nv * nv;
-                fn += nv * __bfloat162float(fr[i]);
+                fn += nv * ldf(fr + i);
             }
             ninv[k] = rsqrtf(warp_sum(nn));
             const float cn = warp_sum(fn) * finv * ninv[k];
@@ -569,17 +575,17 @@ __global__ void __launch_bounds__(512) loss_kernel(const LossParams p) {
             // dfn = coef_pos * gn + sum_k coef_neg[k] * nn_k ;  df = (dfn - fn <fn, dfn>) * finv
             float dot = 0.f;
             for (int i = lane; i < D; i += 32) {
-                float d = coef_pos * ginv * __bfloat162float(gr[i]);
+                float d = coef_pos * ginv * ldf(gr + i);
                 for (int k = 0; k < K; ++k)
-                    d += coef_neg[k] * ninv[k] * __bfloat162float(p.g[(static_cast<long>(B) + static_cast<long>(b) * K + k) * D + i]);
-                dot += d * __bfloat162float(fr[i]) * finv;
+                    d += coef_neg[k] * ninv[k] * ldf(p.g + (static_cast<long>(B) + static_cast<long>(b) * K + k) * D + i);
+                dot += d * ldf(fr + i) * finv;
             }
             dot = warp_sum(dot);
             for (int i = lane; i < D; i += 32) {
-                float d = coef_pos * ginv * __bfloat162float(gr[i]);
+                float d = coef_pos * ginv * ldf(gr + i);
                 for (int k = 0; k < K; ++k)
-                    d += coef_neg[k] * ninv[k] * __bfloat162float(p.g[(static_cast<long>(B) + static_cast<long>(b) * K + k) * D + i]);
-                p.df[static_cast<long>(b) * D + i] = __float2bfloat16((d - __bfloat162float(fr[i]) * finv * dot) * finv);
+                    d += coef_neg[k] * ninv[k] * ldf(p.g + (static_cast<long>(B) + static_cast<long>(b) * K + k) * D + i);
+                stf(p.df + static_cast<long>(b) * D + i, (d - ldf(fr + i) * finv * dot) * finv);
             }
         }
         // multilabel soft margin row b (labels = identity): -[y log s(c) + (1-y) log s(-c)] = softplus(-c) | softplus(c)
@@ -730,17 +736,27 @@ int tris_resize_bilinear_ac(const float* src, float* dst, long nc, int H, int W,
 int tris_stage1_loss_fwd(const void* f, const void* g, const float* cls, float* out, int B, int D, int K, float w1, float w4, float w5,
                          tris_stream_t stream) {
     if (K > 8) return tris::fail(TRIS_ERR_SHAPE, "stage1_loss: at most 8 negatives per sample (got %d)", K);
-    LossParams p{(const __nv_bfloat16*)f, (const __nv_bfloat16*)g, cls, out, nullptr, nullptr, nullptr, B, D, K, w1, w4, w5};
-    loss_kernel<false><<<1, 512, 0, (cudaStream_t)stream>>>(p);
+    LossParams<__nv_bfloat16> p{(const __nv_bfloat16*)f, (const __nv_bfloat16*)g, cls, out, nullptr, nullptr, nullptr, B, D, K, w1, w4, w5};
+    loss_kernel<false, __nv_bfloat16><<<1, 512, 0, (cudaStream_t)stream>>>(p);
     TRIS_LAUNCH_OK("stage1_loss_fwd");
+    return TRIS_OK;
+}
+
+/* fp32-feature variant of the forward (fp32 parity mode) */
+int tris_stage1_loss_fwd_f32(const float* f, const float* g, const float* cls, float* out, int B, int D, int K, float w1, float w4, float w5,
+                             tris_stream_t stream) {
+    if (K > 8) return tris::fail(TRIS_ERR_SHAPE, "stage1_loss: at most 8 negatives per sample (got %d)", K);
+    LossParams<float> p{f, g, cls, out, nullptr, nullptr, nullptr, B, D, K, w1, w4, w5};
+    loss_kernel<false, float><<<1, 512, 0, (cudaStream_t)stream>>>(p);
+    TRIS_LAUNCH_OK("stage1_loss_fwd_f32");
     return TRIS_OK;
 }
 
 int tris_stage1_loss_bwd(const void* f, const void* g, const float* cls, const float* dout, void* df, float* dcls, int B, int D, int K,
                          float w1, float w4, float w5, tris_stream_t stream) {
     if (K > 8) return tris::fail(TRIS_ERR_SHAPE, "stage1_loss: at most 8 negatives per sample (got %d)", K);
-    LossParams p{(const __nv_bfloat16*)f, (const __nv_bfloat16*)g, cls, nullptr, dout, (__nv_bfloat16*)df, dcls, B, D, K, w1, w4, w5};
-    loss_kernel<true><<<1, 512, 0, (cudaStream_t)stream>>>(p);
+    LossParams<__nv_bfloat16> p{(const __nv_bfloat16*)f, (const __nv_bfloat16*)g, cls, nullptr, dout, (__nv_bfloat16*)df, dcls, B, D, K, w1, w4, w5};
+    loss_kernel<true, __nv_bfloat16><<<1, 512, 0, (cudaStream_t)stream>>>(p);
     TRIS_LAUNCH_OK("stage1_loss_bwd");
     return TRIS_OK;
 }

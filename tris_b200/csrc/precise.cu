@@ -236,6 +236,19 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
     }
 }
 
+// tok[n,0,:] = cls + pos[0]; tok[n,1+p,:] = patch[n*(T-1)+p,:] + pos[1+p]   (CLIP/clip/model.py:436-441)
+__global__ void vit_assemble_f32_kernel(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                        float* __restrict__ tok, int N, int T, int D) {
+    const long total = static_cast<long>(N) * T * D;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(i % D);
+        const long r = i / D;
+        const int t = static_cast<int>(r % T);
+        const long n = r / T;
+        tok[i] = (t == 0 ? cls[d] : patch[(n * (T - 1) + (t - 1)) * D + d]) + pos[t * D + d];
+    }
+}
+
 __global__ void gather_rows_f32_kernel(const float* __restrict__ x, const int* __restrict__ idx, float* __restrict__ out, int rows, int D) {
     const long total = static_cast<long>(rows) * D;
     for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x)
@@ -369,6 +382,12 @@ int tris_attn_f32(const float* qkv, float* out, int n, int L, int heads, int cau
     if (smem > 48 * 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_attn_f32: L=%d too long", L);
     attn_f32_kernel<<<n * heads, 128, smem, (cudaStream_t)stream>>>(qkv, out, L, heads, causal);
     TRIS_LAUNCH_OK("attn_f32_kernel");
+    return TRIS_OK;
+}
+
+int tris_vit_assemble_f32(const float* patch, const float* cls, const float* pos, float* tok, int n, int T, int D, tris_stream_t stream) {
+    vit_assemble_f32_kernel<<<grid1d(static_cast<long>(n) * T * D), 256, 0, (cudaStream_t)stream>>>(patch, cls, pos, tok, n, T, D);
+    TRIS_LAUNCH_OK("vit_assemble_f32_kernel");
     return TRIS_OK;
 }
 

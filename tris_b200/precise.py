@@ -107,37 +107,78 @@ class PreciseStage1:
                 x = self.bn(y3, q + "bn3", train, res=x)
         return x                                                            # [B, H/32, W/32, 2048]
 
-    def _ln(self, x, key):
+    def _ln(self, x, key, w=None):
+        w = w or self._w
         y = torch.empty_like(x)
-        L.call("tris_layernorm_f32", _vp(x), _vp(self._w(key + ".weight")), _vp(self._w(key + ".bias")), _vp(y), x.shape[0], x.shape[1],
-               C.c_float(1e-5))
+        L.call("tris_layernorm_f32", _vp(x), _vp(w(key + ".weight")), _vp(w(key + ".bias")), _vp(y), x.shape[0], x.shape[1], C.c_float(1e-5))
         return y
 
-    def text(self, ids):
-        p = self.eng.text.prefix
+    def _blocks(self, x, n, l, prefix, heads, causal, w=None):
+        """12 ResidualAttentionBlocks (CLIP/clip/model.py:366-386) on fp32 rows x [n*l, d]."""
+        w = w or self._w
+        d = x.shape[1]
+        for i in range(12):
+            k = f"{prefix}transformer.resblocks.{i}."
+            h = self._ln(x, k + "ln_1", w)
+            qkv = sgemm(h, w(k + "attn.in_proj_weight"), n * l, 3 * d, d, bias=w(k + "attn.in_proj_bias"))
+            a = torch.empty((n * l, d), device=self.dev, dtype=f32)
+            L.call("tris_attn_f32", _vp(qkv), _vp(a), n, l, heads, int(causal))
+            x1 = sgemm(a, w(k + "attn.out_proj.weight"), n * l, d, d, bias=w(k + "attn.out_proj.bias"), res=x)
+            h2 = self._ln(x1, k + "ln_2", w)
+            u = sgemm(h2, w(k + "mlp.c_fc.weight"), n * l, 4 * d, d, bias=w(k + "mlp.c_fc.bias"), act=L.ACT_QUICKGELU)
+            x = sgemm(u, w(k + "mlp.c_proj.weight"), n * l, d, 4 * d, bias=w(k + "mlp.c_proj.bias"), res=x1)
+        return x
+
+    def text(self, ids, prefix=None, w=None):
+        """CLIP.encode_text (model.py:552-564) -> hidden fp32 [N, E]."""
+        p = self.eng.text.prefix if prefix is None else prefix
+        w = w or self._w
         n, l = ids.shape
         ids = ids.to(torch.int32).contiguous()
-        E, Ppos = self._w(p + "token_embedding.weight"), self._w(p + "positional_embedding")
+        E, Ppos = w(p + "token_embedding.weight"), w(p + "positional_embedding")
         d = E.shape[1]
         x = torch.empty((n * l, d), device=self.dev, dtype=f32)
         eot = torch.empty((n,), device=self.dev, dtype=torch.int32)
         L.call("tris_embed_f32", _vp(ids), _vp(E), _vp(Ppos), _vp(x), _vp(eot), n, l, d)
-        heads = d // 64
-        for i in range(12):
-            k = f"{p}transformer.resblocks.{i}."
-            h = self._ln(x, k + "ln_1")
-            qkv = sgemm(h, self._w(k + "attn.in_proj_weight"), n * l, 3 * d, d, bias=self._w(k + "attn.in_proj_bias"))
-            a = torch.empty((n * l, d), device=self.dev, dtype=f32)
-            L.call("tris_attn_f32", _vp(qkv), _vp(a), n, l, heads, 1)
-            x1 = sgemm(a, self._w(k + "attn.out_proj.weight"), n * l, d, d, bias=self._w(k + "attn.out_proj.bias"), res=x)
-            h2 = self._ln(x1, k + "ln_2")
-            u = sgemm(h2, self._w(k + "mlp.c_fc.weight"), n * l, 4 * d, d, bias=self._w(k + "mlp.c_fc.bias"), act=L.ACT_QUICKGELU)
-            x = sgemm(u, self._w(k + "mlp.c_proj.weight"), n * l, d, 4 * d, bias=self._w(k + "mlp.c_proj.bias"), res=x1)
+        x = self._blocks(x, n, l, p, d // 64, True, w)
         xe = torch.empty((n, d), device=self.dev, dtype=f32)
         L.call("tris_gather_rows_f32", _vp(x), _vp(eot), _vp(xe), n, d)
-        xn = self._ln(xe, p + "ln_final")
-        proj = self._w(p + "text_projection")                               # [512, E] = [K, N]
+        xn = self._ln(xe, p + "ln_final", w)
+        proj = w(p + "text_projection")                                     # [512, E] = [K, N]
         return sgemm(xn, proj, n, proj.shape[1], d, b_kn=True)
+
+    def vit(self, fg, w):
+        """VisionTransformer.forward (model.py:419-448) on fg fp32 [N,3,224,224] with the aux model's fp32 weights."""
+        n, c, s, _ = fg.shape
+        ps, g = 32, s // 32
+        patches = fg.reshape(n, c, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(n * g * g, c * ps * ps).contiguous()   # layout only
+        wc = w("visual.conv1.weight")
+        d = wc.shape[0]
+        pe = sgemm(patches, wc.view(d, -1), n * g * g, d, c * ps * ps)
+        t = g * g + 1
+        tok = torch.empty((n * t, d), device=self.dev, dtype=f32)
+        L.call("tris_vit_assemble_f32", _vp(pe), _vp(w("visual.class_embedding")), _vp(w("visual.positional_embedding")), _vp(tok), n, t, d)
+        x = self._blocks(self._ln(tok, "visual.ln_pre", w), n, t, "visual.", d // 64, False, w)
+        idx = (torch.arange(n, device=self.dev, dtype=torch.int32) * t).contiguous()
+        xc = torch.empty((n, d), device=self.dev, dtype=f32)
+        L.call("tris_gather_rows_f32", _vp(x), _vp(idx), _vp(xc), n, d)
+        proj = w("visual.proj")
+        return sgemm(self._ln(xc, "visual.ln_post", w), proj, n, proj.shape[1], d, b_kn=True)
+
+    @torch.no_grad()
+    def step_losses(self, aux, img, word_ids, neg_word_ids, w=(1.0, 5.0, 2.0)):
+        """Forward of the whole training step in fp32 (train_stage1.py:320-364): -> (loss, l1, l4, l5) fp32 [4]."""
+        aw = aux._engine().store.p
+        cls, _, _, sig, _ = self.forward(img, word_ids, True)
+        fg = ops.mask_resize_fwd(sig.contiguous(), img.float().contiguous(), 224, 32, want_fg=True)[1]
+        f = self.vit(fg, aw)
+        k = 0 if neg_word_ids is None else neg_word_ids.shape[1]
+        ids = word_ids if k == 0 else torch.cat([word_ids, neg_word_ids.reshape(-1, word_ids.shape[1])], 0)
+        g = self.text(ids, prefix="", w=aw)
+        out = torch.empty(4, device=self.dev, dtype=f32)
+        L.call("tris_stage1_loss_fwd_f32", _vp(f), _vp(g), _vp(cls), _vp(out), img.shape[0], f.shape[1], k, C.c_float(w[0]), C.c_float(w[1]),
+               C.c_float(w[2]))
+        return out
 
     # ------------------------------------------------------------------ head (model_stage1.py:61-119, attn.py:111-136)
     def _l2(self, x):
