@@ -127,3 +127,22 @@ def test_adamw_and_poly_lr_match_torch():
         opt.step(); sched.step()
         q, m, v = O.adamw_step(q, g, m, v, it + 1, 5e-5 * O.poly_lr(it, 100))
     assert rel(q, p.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["s224_b2_fuse", "s320_b2_nofuse", "s384_b1_fuse"])
+def test_oracle_matches_reference_on_configuration_edges(case):
+    """224 / 384 inputs and --attn_multi 0: oracle vs tests/golden/variants_golden.npz (unmodified reference, CPU;
+    tests/golden/make_golden_variants.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variants_golden.npz"))
+    size, b, attn = g[case + "/meta"]
+    size, b, s = int(size), int(b), int(g["sub"][0])
+    torch.set_num_threads(8)
+    sd = W.make_tris_state_dict(0)
+    img, ids, _ = W.synthetic_batch(b, size, 20, 0, 77)
+    with torch.no_grad():
+        cls, fg, relu, sig, _ = O.tris_forward(sd, img, ids, True, {}, attn_multi=float(attn))
+        ev = O.tris_forward(sd, img, ids, False, None, attn_multi=float(attn))
+    assert rel(cls, g[case + "/cls_out"]) < 1e-4 and rel(fg, g[case + "/cls_fg"]) < 1e-4
+    assert rel(relu[:, :, ::s, ::s], g[case + "/relu_sub"]) < 1e-4 and rel(sig[:, :, ::s, ::s], g[case + "/sig_sub"]) < 1e-4
+    assert rel(ev[:, :, ::s, ::s], g[case + "/eval_relu_sub"]) < 1e-4

@@ -101,3 +101,27 @@ def test_rn101_backbone_wiring():
     with torch.no_grad():
         out = m(img, ids)
     assert out.shape == (1, 1, 224, 224) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("case", ["s224_b2_fuse", "s320_b2_nofuse", "s384_b1_fuse"])
+def test_fp32_mode_vs_reference_golden_on_configuration_edges(weights, case):
+    """fp32 parity mode straight against the unmodified reference's outputs (tests/golden/variants_golden.npz)."""
+    import os
+    import numpy as np
+    from oracle import weights as W
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variants_golden.npz"))
+    size, b, attn = g[case + "/meta"]
+    size, b, s = int(size), int(b), int(g["sub"][0])
+    m = build(weights, attn_multi=float(attn)).set_precision("fp32")
+    img, ids, _ = W.synthetic_batch(b, size, 20, 0, 77)
+    img, ids = img.cuda(), ids.cuda()
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    with torch.no_grad():
+        m.train()
+        cls, fg, relu, sig, _ = m(img, ids)
+        m.eval()
+        ev = m(img, ids)
+    for name, got, ref in (("cls_out", cls, g[case + "/cls_out"]), ("cls_fg", fg, g[case + "/cls_fg"]),
+                           ("relu", relu[:, :, ::s, ::s], g[case + "/relu_sub"]), ("sig", sig[:, :, ::s, ::s], g[case + "/sig_sub"]),
+                           ("eval relu", ev[:, :, ::s, ::s], g[case + "/eval_relu_sub"])):
+        assert rel(got, t(ref)) < 1e-3, (case, name, rel(got, t(ref)))

@@ -74,3 +74,41 @@ class Stage1Inference:
         f = f / f.norm(dim=-1, keepdim=True)
         g = g / g.norm(dim=-1, keepdim=True)
         return f @ g.t()
+
+
+class AsyncCamWriter:
+    """Background `.npy` writer for the PRMS / CAM dump (validate.py:354-359, file name `{idx}_{img_id}.npy`, consumed by the
+    IRNet stage): the map is copied to pinned host memory on a copy stream and written by a worker thread, so that disk I/O
+    and the D2H copy do not stall the inference loop."""
+
+    def __init__(self, out_dir, workers=2):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(out_dir, exist_ok=True)
+        self.out_dir, self.pool, self.pending = out_dir, ThreadPoolExecutor(max_workers=workers), []
+        self.stream = torch.cuda.Stream()
+        self.names = []
+
+    def submit(self, name, cam):
+        import os
+        import numpy as np
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            host = torch.empty(cam.shape, dtype=cam.dtype, pin_memory=True)
+            host.copy_(cam, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        cam.record_stream(self.stream)
+        path = os.path.join(self.out_dir, name + ".npy")
+
+        def work():
+            ev.synchronize()
+            np.save(path, host.numpy())
+        self.pending.append(self.pool.submit(work))
+        self.names.append(name)
+
+    def close(self):
+        for f in self.pending:
+            f.result()
+        self.pool.shutdown()
+        return self.names

@@ -80,6 +80,8 @@ def validate_same_sentence(args, refs, model, aux, local_rank=0):
     """PRMS map selection (validate.py:253-387) with per-ref de-duplicated encoders."""
     from tris_b200.infer import Stage1Inference
     inf = Stage1Inference(model, aux, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
+    from tris_b200.infer import AsyncCamWriter
+    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
     ious, names = [], []
     for idx, img, word_ids, target in refs:
         img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
@@ -91,10 +93,10 @@ def validate_same_sentence(args, refs, model, aux, local_rank=0):
         cam = _to_original(cams[best:best + 1], target.shape[-2:])[0, 0]
         iou, _, cam = _iou_hit(cam, target[0])
         ious.append(iou)
-        if args.save_cam and args.cam_save_dir:
-            os.makedirs(args.cam_save_dir, exist_ok=True)
-            np.save(os.path.join(args.cam_save_dir, f"{idx}_{idx}.npy"), cam.cpu().numpy())      # {idx}_{img_id}.npy
-            names.append(f"{idx}_{idx}")
+        if writer is not None:
+            writer.submit(f"{idx}_{idx}", cam)                                   # {idx}_{img_id}.npy, written in the background
+    if writer is not None:
+        names = writer.close()
     if args.save_cam and args.name_save_dir:
         os.makedirs(args.name_save_dir, exist_ok=True)
         json.dump(names, open(os.path.join(args.name_save_dir, f"{args.dataset}_train_names.json"), "w"))
