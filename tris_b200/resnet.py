@@ -3,9 +3,11 @@
 Arithmetic restated from CLIP/clip/model.py:10-55 (Bottleneck), :212-232 + :254-279 (stem / layers) of the reference;
 the attention pool (:58-104) is NOT computed here -- Stage-1 discards it (model_stage1.py:59).
 
-Every conv is a tcgen05 GEMM (gemm.py); the first stem conv goes through an im2col of the fp32 NCHW image; the two
-32-channel stem activations are carried zero-padded to 64 channels so that every k-block is a full 128-byte TMA row.
-BatchNorm batch statistics come out of the GEMM epilogues; BN-apply/ReLU/pool/residual are one streaming kernel.
+Every conv is a tcgen05 GEMM (gemm.py); the first stem conv goes through an im2col of the fp32 NCHW image.  The two
+32-channel stem activations must fill 128-byte TMA rows: even batches pack the image pair (2i, 2i+1) into one 64-channel
+row with block-diagonal weights (half the pixels, no padding, BatchNorm sums of the two halves folded); odd batches carry
+them zero-padded to 64 channels.  BatchNorm batch statistics come out of the GEMM epilogues; BN-apply/ReLU/pool/residual
+are one streaming kernel.  In backward the weight gradients (leaves of the chain) run on a side stream.
 """
 from __future__ import annotations
 
