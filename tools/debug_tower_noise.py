@@ -13,7 +13,10 @@ eng = m.engine(); eng.ensure_fresh(True)
 img, ids, _ = W.synthetic_batch(B, 320, 20, 3, 4321)
 img = img.cuda()
 rn, pr = eng.resnet, PreciseStage1(m)
-def frob(a, b): return ((a.double() - b.double()).norm() / b.double().norm()).item()
+def frob(a, b):
+    a, b = a.double(), b.double()
+    proj = (a * b).sum() / (b * b).sum()          # least-squares gain of the bf16 tensor on the fp32 one (1 = unbiased)
+    return f"{((a - b).norm() / b.norm()).item():.4f}  gain {proj.item():.5f}  mean ratio {(a.mean() / b.mean()).item():.5f}"
 with torch.no_grad():
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     so = [0]; rn.stats_buf.zero_()
@@ -24,7 +27,7 @@ with torch.no_grad():
     xr = pr.bn(pr.conv3x3(img, p + "conv1.weight", stride=2, nchw=True), p + "bn1", True)
     xr = pr.bn(pr.conv3x3(xr, p + "conv2.weight"), p + "bn2", True)
     xr = pr.avgpool(pr.bn(pr.conv3x3(xr, p + "conv3.weight"), p + "bn3", True))
-    print(f"stem        {frob(x.float(), xr):.4f}")
+    print(f"stem        {frob(x.float(), xr)}")
     for blk in rn.blocks:
         x, _ = rn._block_fwd(blk, x, True, stats)
         q = blk.p
@@ -37,5 +40,5 @@ with torch.no_grad():
             xr = pr.bn(y3, q + "bn3", True, y1=pr.conv1x1(idt, q + "downsample.0.weight"), key1=q + "downsample.1")
         else:
             xr = pr.bn(y3, q + "bn3", True, res=xr)
-        print(f"{q[len(p):]:12s}{frob(x.float(), xr):.4f}")
+        print(f"{q[len(p):]:12s}{frob(x.float(), xr)}")
     m.load_state_dict(sd0)
