@@ -1,4 +1,5 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the oracle port of the reference training step on the host cores)
+"""CPU: the reference arm of bench.py (`--impl reference`: the unmodified reference step on the host cores when a copy of the
+reference is present -- /root/reference or baseline/_ref -- else the oracle port)
 prints ONE JSON line with the contract's keys; under a 2-rank launch only rank 0 prints."""
 import json
 import os
@@ -11,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
+    env.setdefault("TRIS_CPU_ARM_MAX_BATCH", "4")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--gpus",
                         env.get("WORLD_SIZE", "1")], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -27,7 +29,7 @@ def test_reference_arm_json_contract():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
