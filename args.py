@@ -43,6 +43,9 @@ def get_parser():
     p.add_argument("--text", default=None, type=str)
     # ---- additions of this build
     p.add_argument("--synthetic", action="store_true", help="synthetic RefCOCOg-shaped data (the only source offline)")
+    p.add_argument("--synthetic-weights", "--synthetic_weights", dest="synthetic_weights", action="store_true",
+                   help="allow randomly initialised CLIP backbones when no checkpoint file is found (there is no download "
+                        "path offline); without it a missing checkpoint is an error, like in the reference")
     p.add_argument("--steps_per_epoch", default=50, type=int)
     p.add_argument("--val_refs", default=64, type=int)
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = forward-only parity mode (validate/demo)")

@@ -88,7 +88,7 @@ class ClockSampler:
 
 
 def make_args():
-    return argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024,
+    return argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024,
                               attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 
 
@@ -256,7 +256,7 @@ def run_gpu_arm(a):
         for k, p in model.named_parameters():
             if k.endswith("bn3.weight") and "layer" in k:
                 p.uniform_(0.1, 0.3)
-    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True)
     trainer = Stage1Trainer(model, aux, max_iter=100000)
     n_pool = 3
     host = [synthetic_batch(B, 320, 20, 3, seed=1234 + rank * 1000 + i, pin=True) for i in range(n_pool)]

@@ -46,7 +46,6 @@ def prepare(args):
 
 
 def main(args):
-    warnings.simplefilter("ignore")
     from tris_b200 import ops
     from tris_b200.model_stage1 import TRIS
     img, ids, (h, w) = prepare(args)
@@ -68,5 +67,8 @@ if __name__ == "__main__":
     p.add_argument("--token_ids", default=None, type=str)
     a = p.parse_args()
     if a.size == 384:
+        # the reference's demo.py ignores --size (argparse default 384) and resizes to its module constant img_size = 320
+        # (demo.py:64); do the same, but say so
+        print("demo.py: --size left at the argparse default 384 -> using 320 like the reference demo (pass --size explicitly to override)")
         a.size = 320
     main(a)

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# parity tests build randomly initialised models and load oracle.weights state_dicts into them: the explicit opt-in that
+# tris_b200.clip_model.load requires when no CLIP checkpoint file is present (see its docstring)
+os.environ.setdefault("TRIS_ALLOW_RANDOM_INIT", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -38,6 +38,7 @@ def _ours(args, seed=0):
     from oracle import weights as W
     from tris_b200 import clip_model
     from tris_b200.model_stage1 import TRIS
+    args.synthetic_weights = True
     model = TRIS(args)
     model.load_state_dict(W.make_tris_state_dict(seed), strict=True)
     model = model.cuda()
@@ -82,8 +83,13 @@ def _run_validate(ns, args, model, loader, aux=None, prms=False, out_dir=None):
     args.name_save_dir = os.path.join(out_dir, "names")
     args.print_freq = 1000
     if prms:
+        # validate_same_sentence loads its scorer itself (validate.py:282); CLIP.clip is ONE module shared with the TRIS
+        # constructor, so the patch is undone afterwards
         V.clip.load = lambda *a, **k: (aux, None)
-        return V.validate_same_sentence(args, loader, model, 0, save_cam=True)
+        try:
+            return V.validate_same_sentence(args, loader, model, 0, save_cam=True)
+        finally:
+            V.clip.load = ns.fake_load
     return V.validate(args, loader, model, 0, save_cam=True)
 
 

@@ -319,7 +319,7 @@ def test_vit_tower_fwd_dgrad_vs_oracle():
     from tris_b200 import clip_model
     from tris_b200.engine import patchify
     aux_sd = W.make_vitb32_clip_state_dict(7, cos_bias=True)
-    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True)
     aux.load_state_dict(aux_sd)
     img = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(3))
     x = img.cuda().requires_grad_(True)

@@ -74,7 +74,7 @@ def test_fp32_step_losses_vs_reference(setup, golden):
     from tris_b200 import clip_model
     from tris_b200.precise import PreciseStage1
     b, size, l, neg, sub, s_tris, s_aux, s_data = [int(v) for v in golden["meta"]]
-    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=l)
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=l, allow_random_init=True)
     aux.load_state_dict(W.make_vitb32_clip_state_dict(s_aux, cos_bias=True), strict=True)
     _, _, negs = W.synthetic_batch(b, size, l, neg, s_data)
     m = setup["model"].train()

@@ -34,7 +34,7 @@ def setup(golden):
     model = TRIS(make_args())
     model.load_state_dict(W.make_tris_state_dict(s_tris), strict=True)
     model = model.cuda()
-    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=l)
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=l, allow_random_init=True)
     aux.load_state_dict(W.make_vitb32_clip_state_dict(s_aux, cos_bias=True), strict=True)
     img, ids, negs = W.synthetic_batch(b, size, l, neg, s_data)
     return dict(model=model, aux=aux, img=img.cuda(), ids=ids.cuda(), negs=negs.cuda(), sub=sub)

@@ -76,7 +76,7 @@ def test_step_without_negatives_and_without_fusion(weights):
     from tris_b200.train_step import stage1_losses
     m = build(weights, attn_multi=0.0).train()
     assert not hasattr(m, "attn_fusion") and len(m.state_dict()) < 518
-    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+    aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True)
     aux.load_state_dict(W.make_vitb32_clip_state_dict(7, cos_bias=True), strict=True)
     img, ids, _ = W.synthetic_batch(4, 224, 20, 0, 5)
     losses = stage1_losses(m, aux, img.cuda(), ids.cuda(), None)

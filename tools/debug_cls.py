@@ -7,7 +7,7 @@ from oracle import tris_oracle as O
 from oracle import weights as W
 from tris_b200.model_stage1 import TRIS
 bf16 = torch.bfloat16
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 sd = W.make_tris_state_dict(0)
 m = TRIS(args); m.load_state_dict(sd); m = m.cuda().train(); eng = m.engine(); eng.ensure_fresh(True)
 img, ids, negs = W.synthetic_batch(3, 320, 20, 3, 1234)

@@ -10,7 +10,7 @@ def rel(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item(), ((a - b).norm() / (b.norm() + 1e-12)).item()
 
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 train = "--eval" not in sys.argv
 B = 3
 sd = W.make_tris_state_dict(0)

@@ -10,7 +10,7 @@ def d(a, b):
     a, b = a.double(), b.double()
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 sd = W.make_tris_state_dict(0)
 img, ids, negs = W.synthetic_batch(3, 320, 20, 3, 1234)
 m = TRIS(args); m.load_state_dict(sd); m = m.cuda().train()

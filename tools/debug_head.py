@@ -21,7 +21,7 @@ def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
 ap = argparse.ArgumentParser(); ap.add_argument("--B", type=int, default=4); ap.add_argument("--nofuse", action="store_true")
 ap.add_argument("--which", default="both")
 a = ap.parse_args()
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024,
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024,
                           attn_multi=0.0 if a.nofuse else 0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 sd = W.make_tris_state_dict(0)
 g = torch.Generator().manual_seed(3)

@@ -9,10 +9,10 @@ from tris_b200 import clip_model
 from tris_b200.model_stage1 import TRIS
 from tris_b200.train_step import stage1_losses
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 48
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 sd = W.make_tris_state_dict(0); aux_sd = W.make_vitb32_clip_state_dict(7, cos_bias=True)
 m = TRIS(args); m.load_state_dict(sd); m = m.cuda().train()
-aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20); aux.load_state_dict(aux_sd, strict=True)
+aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True); aux.load_state_dict(aux_sd, strict=True)
 img, ids, negs = W.synthetic_batch(B, 320, 20, 3, 1234)
 sdc = {k: v.cuda() for k, v in sd.items()}; auxc = {k: v.cuda() for k, v in aux_sd.items()}
 with torch.no_grad():

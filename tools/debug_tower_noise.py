@@ -7,7 +7,7 @@ from oracle import weights as W
 from tris_b200.model_stage1 import TRIS
 from tris_b200.precise import PreciseStage1
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-args = argparse.Namespace(bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
+args = argparse.Namespace(synthetic_weights=True, bert_tokenizer="clip", backbone="clip-RN50", max_query_len=20, hidden_dim=1024, attn_multi=0.1, FOCAL_P=3, FOCAL_LAMBDA=0.01)
 m = TRIS(args); m.load_state_dict(W.make_tris_state_dict(0)); m = m.cuda().train()
 eng = m.engine(); eng.ensure_fresh(True)
 img, ids, _ = W.synthetic_batch(B, 320, 20, 3, 4321)

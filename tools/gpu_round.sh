@@ -8,10 +8,10 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | 
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" != "quick" ]; then
-timeout 300 python train_stage1.py --synthetic --batch_size 48 --size 320 --max_query_len 20 --negative_samples 3 --epoch 1 --steps_per_epoch 20 --print-freq 10 --val_refs 8 > gpurun_out/train_entry.txt 2>&1; tail -4 gpurun_out/train_entry.txt
-timeout 300 python validate.py --synthetic --size 320 --max_query_len 20 --val_refs 200 > gpurun_out/validate_entry.txt 2>&1; tail -2 gpurun_out/validate_entry.txt
-timeout 300 python validate.py --synthetic --size 320 --max_query_len 20 --val_refs 200 --prms >> gpurun_out/validate_entry.txt 2>&1; tail -1 gpurun_out/validate_entry.txt
-timeout 120 python demo.py --synthetic --output gpurun_out/demo_cam.npy > gpurun_out/demo_entry.txt 2>&1; tail -1 gpurun_out/demo_entry.txt
+timeout 300 python train_stage1.py --synthetic --synthetic-weights --batch_size 48 --size 320 --max_query_len 20 --negative_samples 3 --epoch 1 --steps_per_epoch 20 --print-freq 10 --val_refs 8 > gpurun_out/train_entry.txt 2>&1; tail -4 gpurun_out/train_entry.txt
+timeout 300 python validate.py --synthetic --synthetic-weights --size 320 --max_query_len 20 --val_refs 200 > gpurun_out/validate_entry.txt 2>&1; tail -2 gpurun_out/validate_entry.txt
+timeout 300 python validate.py --synthetic --synthetic-weights --size 320 --max_query_len 20 --val_refs 200 --prms >> gpurun_out/validate_entry.txt 2>&1; tail -1 gpurun_out/validate_entry.txt
+timeout 120 python demo.py --synthetic --synthetic-weights --output gpurun_out/demo_cam.npy > gpurun_out/demo_entry.txt 2>&1; tail -1 gpurun_out/demo_entry.txt
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches.csv gpurun_out/gemm_traffic.json > gpurun_out/launch_summary.txt 2>&1
 head -30 gpurun_out/launch_summary.txt

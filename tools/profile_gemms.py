@@ -10,7 +10,7 @@ from tris_b200.synthetic import synthetic_batch
 from tris_b200.train_step import Stage1Trainer
 
 model = TRIS(make_args()).cuda().train()
-aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True)
 tr = Stage1Trainer(model, aux, max_iter=1000)
 batch = tuple(t.cuda() for t in synthetic_batch(48, 320, 20, 3, 1))
 for _ in range(2):

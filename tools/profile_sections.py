@@ -16,7 +16,7 @@ with torch.no_grad():
     for k, p in model.named_parameters():
         if k.endswith("bn3.weight") and "layer" in k:
             p.uniform_(0.1, 0.3)
-aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20)
+aux, _ = clip_model.load("ViT-B/32", device="cuda", txt_length=20, allow_random_init=True)
 tr = Stage1Trainer(model, aux, max_iter=1000)
 img, ids, negs = (t.cuda() for t in synthetic_batch(B, 320, 20, 3, 1))
 eng, aeng = model.engine(), aux._engine()

@@ -44,6 +44,7 @@ def ref_loss(model, aux, img, ids, neg):
 rows = []
 model, aux = RS.build_models(ns, args, "cuda", aux_half=False)
 sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+args.synthetic_weights = True
 ours = TRIS(args)
 ours.load_state_dict(W.make_tris_state_dict(0), strict=True)
 ours = ours.cuda().train()

@@ -24,7 +24,6 @@ from args import get_parser  # noqa: E402
 
 
 def main(args):
-    warnings.simplefilter("ignore")
     from tris_b200 import clip_model as clip
     from tris_b200 import dp
     from tris_b200.model_stage1 import TRIS
@@ -42,10 +41,20 @@ def main(args):
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
         print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
-    aux, _ = clip.load("ViT-B-32", device="cuda", jit=False, txt_length=args.max_query_len)
+    aux, _ = clip.load("ViT-B-32", device="cuda", jit=False, txt_length=args.max_query_len,
+                       allow_random_init=args.synthetic_weights)
+    warnings.simplefilter("ignore")      # only now: model construction / weight loading must stay loud
     max_iter = args.steps_per_epoch * args.epoch
     trainer = Stage1Trainer(model, aux, max_iter=max_iter, lr=args.lr, lr_multi=args.lr_multi, weight_decay=args.weight_decay,
                             w=(args.w1, args.w4, args.w5))
+    if args.resume and args.pretrain and "optimizer" in ck:
+        # utils/util.py:81-96 of the reference: resume restores optimizer + lr_scheduler + start_epoch
+        trainer.load_state_dict(ck, start_step=args.start_epoch * args.steps_per_epoch if args.start_epoch else None)
+        if not args.start_epoch:
+            args.start_epoch = int(ck.get("epoch", -1)) + 1
+        print(f"resume: optimizer state restored, step {int(trainer.step_count.item())}, start_epoch {args.start_epoch}")
+    elif args.start_epoch:
+        trainer.step_count.fill_(args.start_epoch * args.steps_per_epoch)      # schedule position without stored moments
     B, k = args.batch_size, args.negative_samples
     # a small pool of pinned synthetic batches, re-used round-robin (generating 48 x 3 x 320 x 320 normals on the host costs
     # more than the whole GPU step); each step still pays the H2D copy like a real DataLoader(pin_memory=True) batch
@@ -76,7 +85,9 @@ def main(args):
             if args.output and miou > best:
                 best = miou
                 os.makedirs(args.output, exist_ok=True)
-                torch.save({"model": model.state_dict(), "epoch": epoch}, os.path.join(args.output, f"stage1_best_{epoch}.pth"))
+                # same keys as the reference's save_checkpoint (utils/util.py:50-77): model, optimizer, lr_scheduler, epoch
+                torch.save({"model": model.state_dict(), "epoch": epoch, **trainer.state_dict()},
+                           os.path.join(args.output, f"stage1_best_{epoch}.pth"))
         model.train()
     if world > 1:
         dist.destroy_process_group()

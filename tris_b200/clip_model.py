@@ -86,12 +86,14 @@ def _find_checkpoint(name: str, download_root=None):
 
 
 def load(name: str, device="cuda" if torch.cuda.is_available() else "cpu", jit: bool = False, download_root: str = None,
-         txt_length: int = 77):
+         txt_length: int = 77, allow_random_init: bool = None):
     """Same signature / return convention as the reference's ``clip.load`` -> (model, preprocess).
 
     Accepts both "ViT-B/32" and the reference's "ViT-B-32" spelling (train_stage1.py:167).  Looks for an
-    OpenAI checkpoint on disk (state_dict or TorchScript archive); there is no download path in this build, so if no
-    file is found the model keeps its reference-style random initialisation and a warning is emitted.
+    OpenAI checkpoint on disk (state_dict or TorchScript archive).  There is no download path in this build: like the
+    reference (which downloads or raises, clip.py:122-127) a missing checkpoint is an ERROR, unless random initialisation
+    is asked for explicitly -- ``allow_random_init=True`` (synthetic benchmarks / parity tests that load their own
+    state_dict afterwards, drivers run with ``--synthetic-weights``) or the environment variable TRIS_ALLOW_RANDOM_INIT=1.
     """
     kind = _canonical(name)
     model = CLIPModel(kind, txt_length=txt_length)
@@ -107,6 +109,12 @@ def load(name: str, device="cuda" if torch.cuda.is_available() else "cpu", jit: 
         if missing.missing_keys:
             warnings.warn(f"clip.load({name}): missing keys {missing.missing_keys[:4]}...")
     else:
-        warnings.warn(f"clip.load({name}): no checkpoint file found (offline build) - using random initialisation")
+        if allow_random_init is None:
+            allow_random_init = os.environ.get("TRIS_ALLOW_RANDOM_INIT", "0") == "1"
+        if not allow_random_init:
+            raise RuntimeError(
+                f"clip.load({name!r}): no checkpoint file found (looked for {_FILES[kind]} in download_root, ~/.cache/clip and '.'); "
+                "this build cannot download weights.  Pass a checkpoint path, or opt in to random initialisation with "
+                "allow_random_init=True / --synthetic-weights / TRIS_ALLOW_RANDOM_INIT=1")
     model = model.to(device).eval()
     return model, None

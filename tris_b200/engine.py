@@ -38,6 +38,7 @@ class _EngineBase:
         self.fwd_id = 0
         self.last_bwd_id = -1
         self._seen_versions = None
+        self.derived_stale = True
         self.extra_grad_keys = []
 
     # ---- shadow maintenance
@@ -45,12 +46,19 @@ class _EngineBase:
         return sum(p._version for p in self.store.params.values())
 
     def ensure_fresh(self, force=False):
+        """bf16 shadow + derived operands (packed 3x3 / stem weights, padded BN vectors) follow the fp32 masters.
+        The shadow is re-cast only when a master changed behind it (torch-side update: param._version moved, or a load);
+        the fused AdamW rewrites the shadow itself and only flags ``derived_stale``.  ``force`` (every training forward)
+        re-derives the packed operands unconditionally so that a captured CUDA graph re-derives them on every replay."""
         v = self._versions()
-        if force or v != self._seen_versions or not self.store.shadow_valid:
+        stale = v != self._seen_versions or not self.store.shadow_valid
+        if stale or force or self.derived_stale:
             with torch.no_grad():
-                self.store.refresh_shadow()
+                if stale:
+                    self.store.refresh_shadow()
                 self.refresh_derived()
             self._seen_versions = self._versions()
+            self.derived_stale = False
 
     def refresh_derived(self):
         pass

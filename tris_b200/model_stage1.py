@@ -29,7 +29,10 @@ class TRIS(nn.Module):
         else:
             raise ValueError(f"Stage-1 TRIS supports clip-RN50 / clip-RN101 only (got {args.backbone}); SURVEY F4")
         kind = args.backbone.split("-")[-1]
-        clip_model, _ = clip.load(kind, device="cpu", jit=False, txt_length=args.max_query_len)
+        # random-init backbone only on explicit request (args.synthetic_weights / TRIS_ALLOW_RANDOM_INIT=1): the reference's
+        # clip.load downloads the OpenAI weights or raises (CLIP/clip/clip.py:122-127)
+        clip_model, _ = clip.load(kind, device="cpu", jit=False, txt_length=args.max_query_len,
+                                  allow_random_init=getattr(args, "synthetic_weights", None))
         self.backbone = clip_model.float()
         entries = S.tris_head_spec(args.hidden_dim, self.textdim, last_vis_channel)
         if not args.attn_multi > 0:

@@ -89,7 +89,9 @@ class Stage1Trainer:
                C.c_long(st.group_bounds[1]), C.c_void_p(self.step_count.data_ptr()), C.c_float(self.max_iter),
                C.c_float(self.lr * self.lr_multi), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8),
                C.c_float(self.wd), C.c_float(1.0 / self.world), C.c_float(0.9), launches=2)
-        self.eng._seen_versions = None   # masters changed behind torch's back: re-derive packed operands next forward
+        # masters changed behind torch's back; the kernel rewrote the bf16 shadow too, so only the derived operands (packed
+        # 3x3 / stem weights, padded BN vectors) must be re-derived by the next forward -- train OR eval
+        self.eng.derived_stale = True
 
     def _fwd_bwd(self, img, word_ids, neg_word_ids):
         self.model.train()
@@ -115,12 +117,19 @@ class Stage1Trainer:
         self.graph.replay()
         if self.world > 1:            # the NCCL all-reduce + AdamW stay outside the graph in multi-rank runs
             self.optimizer_step()
+        # the replayed AdamW ran AFTER the replayed re-derivation of the packed operands: an eval forward that follows
+        # (validate after each epoch) must re-derive them from the updated masters
+        self.eng.derived_stale = True
         return s_out
 
     def capture(self, img, word_ids, neg_word_ids, warmup=3):
         """Capture the whole step (fwd + bwd + all-reduce + AdamW) into one CUDA graph (static shapes)."""
         s_img, s_ids = img.clone(), word_ids.clone()
         s_neg = neg_word_ids.clone() if neg_word_ids is not None else None
+        # the warm-up steps below are real optimizer steps on one batch: snapshot everything they mutate (masters, Adam
+        # moments, step counter, BatchNorm running statistics) and put it back, so that capture() is invisible to the
+        # training trajectory and to the poly-LR schedule
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -132,6 +141,48 @@ class Stage1Trainer:
         with torch.cuda.graph(g):
             out = self._step_eager(s_img, s_ids, s_neg) if self.world == 1 else self._fwd_bwd(s_img, s_ids, s_neg)
         self.graph, self.static = g, (s_img, s_ids, s_neg, out)
+        self._restore(snap)
+        return self
+
+    # ---- state (checkpoint / resume; utils/util.py:50-96 of the reference stores 'optimizer' and 'lr_scheduler')
+    def _snapshot(self):
+        st = self.eng.store
+        bufs = [b for b in self.model.buffers()]
+        return {"flat": st.flat.clone(), "m": self.m.clone(), "v": self.v.clone(), "step": self.step_count.clone(),
+                "bufs": [b.clone() for b in bufs]}
+
+    def _restore(self, snap):
+        st = self.eng.store
+        with torch.no_grad():
+            st.flat.copy_(snap["flat"]); self.m.copy_(snap["m"]); self.v.copy_(snap["v"]); self.step_count.copy_(snap["step"])
+            for b, s in zip(self.model.buffers(), snap["bufs"]):
+                b.copy_(s)
+            # masters were rewritten by a plain copy: re-cast the shadow NOW (a captured graph only re-derives the packed
+            # operands, the fused AdamW keeps the shadow current from here on)
+            st.refresh_shadow()
+            self.eng.refresh_derived()
+        self.eng._seen_versions = self.eng._versions()
+        self.eng.derived_stale = True
+        torch.cuda.synchronize()
+
+    def state_dict(self):
+        """{'optimizer': Adam moments as flat fp32 tensors over the trainable prefix + step, 'lr_scheduler': schedule position}."""
+        return {"optimizer": {"exp_avg": self.m.detach().cpu(), "exp_avg_sq": self.v.detach().cpu(), "step": int(self.step_count.item()),
+                              "lr": self.lr, "lr_multi": self.lr_multi, "weight_decay": self.wd, "n_train": int(self.m.numel())},
+                "lr_scheduler": {"last_epoch": int(self.step_count.item()), "max_iter": self.max_iter}}
+
+    def load_state_dict(self, sd, start_step=None):
+        """Restore Adam moments and the step counter (bias correction + poly-0.9 schedule position).  ``start_step``
+        overrides the stored step (resume at --start_epoch N: N * steps_per_epoch).  Call it BEFORE capture(): the
+        schedule length is a launch argument baked into the captured graph."""
+        opt = sd["optimizer"]
+        if int(opt["n_train"]) != self.m.numel():
+            raise ValueError(f"optimizer state holds {opt['n_train']} elements, the model has {self.m.numel()} trainable")
+        self.m.copy_(opt["exp_avg"].to(self.m.device)); self.v.copy_(opt["exp_avg_sq"].to(self.v.device))
+        step = int(opt["step"]) if start_step is None else int(start_step)
+        self.step_count.fill_(step)
+        if "lr_scheduler" in sd and sd["lr_scheduler"].get("max_iter"):
+            self.max_iter = float(sd["lr_scheduler"]["max_iter"])
         return self
 
 

@@ -104,7 +104,6 @@ def validate_same_sentence(args, refs, model, aux, local_rank=0):
 
 
 def main(args):
-    warnings.simplefilter("ignore")
     import time
     from tris_b200 import clip_model as clip
     from tris_b200 import dp
@@ -120,7 +119,8 @@ def main(args):
     refs = synthetic_refs(args, args.val_refs, rank, world)
     t0 = time.time()
     if args.prms:
-        aux, _ = clip.load("ViT-B/32", device="cuda", jit=False, txt_length=args.max_query_len)
+        aux, _ = clip.load("ViT-B/32", device="cuda", jit=False, txt_length=args.max_query_len,
+                           allow_random_init=args.synthetic_weights)
         miou = validate_same_sentence(args, refs, model, aux, rank)
         torch.cuda.synchronize()
         print(f"rank {rank}: PRMS mIoU {miou:.4f}  {len(dp.shard_range(args.val_refs, rank, world)) / (time.time() - t0):.1f} refs/s")
