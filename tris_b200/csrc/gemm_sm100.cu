@@ -165,7 +165,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 0 || warp == 10) {
         // ------------------------------------------------------------------ TMA producers: warp 0 feeds A, warp 10 feeds B
         // (two single-thread issue loops in parallel; each arms the stage's full barrier with its own byte count)
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             const bool is_a = warp == 0;
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -252,8 +252,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ UMMA issuer (single thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ UMMA issuer (single elected thread)
+        if (ptx::elect_one()) {
             uint32_t stage = 0, phase = 0;
             uint32_t acc_phase = 0;   // bit b = phase of accumulator buffer b
             int it = 0;
@@ -326,7 +326,9 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const bool rvalid = grow < p.M;
             // One thread polls the mbarrier (256 pollers would saturate the SM's barrier unit and slow the producer /
             // issuer threads); the named barrier then releases the other epilogue warps.
-            if (tid_e == 0) {
+            // (elected lane of the first epilogue warp: elect.sync always picks the same lane, which therefore also owns the
+            // bulk async-groups of the TMA stores below)
+            if (ew == 0 && ptx::elect_one()) {
                 if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[4 * 64 + it] = clock64();
                 ptx::mbar_wait(ptx::smem_u32(&ctl->acc_full[buf]), (acc_phase >> buf) & 1);
                 if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[5 * 64 + it] = clock64();
@@ -428,7 +430,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             ptx::named_bar_sync(1, 256);
             // ---- TMA store (one elected thread), issued BEFORE the statistics pass: both only read the staged tile, so the
             // store drains while the epilogue warps accumulate the column sums
-            if (tid_e == 0 && !(p.dbg & 4)) {
+            if (ew == 0 && !(p.dbg & 4) && ptx::elect_one()) {
                 for (int g = 0; g < ngroups; ++g) {
                     const int cg = n0 + g * gw;
                     if (cg >= p.N) break;
@@ -495,7 +497,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             if ((p.dbg & 8) && blockIdx.x == 0 && tid_e == 0 && it < 64) p.dbg_buf[6 * 64 + it] = clock64();
         }
-        if (tid_e == 0) ptx::bulk_wait_all();
+        if (ew == 0 && ptx::elect_one()) ptx::bulk_wait_all();
         if (p.stats != nullptr) {
             ptx::named_bar_sync(1, 256);
             for (int i = tid_e; i < 2 * p.N; i += 256) {

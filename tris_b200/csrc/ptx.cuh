@@ -17,6 +17,20 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+// One lane of a fully converged warp.  ptxas treats a region guarded by an ELECT predicate as single-lane, so the operands of
+// UTCHMMA / UTMALDG / UTMASTG / UTCBAR inside it are placed in uniform registers directly.  A plain `if (lane == 0)` is
+// NOT recognised: every such instruction is then wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop, which
+// measured ~140 cycles per tcgen05.mma issue instead of the hardware's 41 + N/2 (tools/micro/mma_rate*.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(p));
+    return p != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
