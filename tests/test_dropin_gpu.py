@@ -82,6 +82,7 @@ def _run_validate(ns, args, model, loader, aux=None, prms=False, out_dir=None):
     args.cam_save_dir = os.path.join(out_dir, "cam")
     args.name_save_dir = os.path.join(out_dir, "names")
     args.print_freq = 1000
+    args.save_cam = True            # validate_same_sentence reads args.save_cam, not its parameter (validate.py:258)
     if prms:
         # validate_same_sentence loads its scorer itself (validate.py:282); CLIP.clip is ONE module shared with the TRIS
         # constructor, so the patch is undone afterwards
