@@ -97,6 +97,8 @@ def load_reference():
     ns = types.SimpleNamespace(TRIS=TRIS, clip=clip, CLIP=CLIP, get_parser=get_parser, fake_load=fake_load)
     try:
         import train_stage1 as T  # noqa
+        import validate as V  # noqa
+        ns.T, ns.V = T, V
         ns.clip_forward, ns.MaxLoss = T.clip_forward, T.MaxLoss
     except Exception as e:  # pragma: no cover - dataset deps missing
         ns.train_import_error = repr(e)
@@ -106,7 +108,38 @@ def load_reference():
         spec.loader.exec_module(mod)
         ns.clip_forward = mod.clip_forward
         ns.MaxLoss = None
+    from CLIP.clip.model import convert_weights  # noqa
+    ns.convert_weights = convert_weights
+    _isolate()
     return ns
+
+
+def _isolate():
+    """The reference's top-level module names (`args`, `validate`, `train_stage1`, `model`, `utils`, ...) collide with this
+    repo's own entry points: once everything is imported, park them under a `tris_reference.` prefix in sys.modules and take
+    the reference root off sys.path, so that a later `import validate` / `from args import ...` finds this repo's files."""
+    root = os.path.realpath(REF_ROOT)
+    for name, mod in list(sys.modules.items()):
+        d = getattr(mod, "__dict__", {})          # (no getattr on the module: lazy modules import things on attribute access)
+        f = d.get("__file__")
+        try:
+            paths = [f] if f else list(d.get("__path__") or [])
+        except Exception:
+            paths = []
+        if any(os.path.realpath(q).startswith(root + os.sep) or os.path.realpath(q) == root for q in paths if isinstance(q, str)):
+            sys.modules["tris_reference." + name] = sys.modules.pop(name)
+    while REF_ROOT in sys.path:
+        sys.path.remove(REF_ROOT)
+
+
+_NS = None
+
+
+def load_reference_once():
+    global _NS
+    if _NS is None:
+        _NS = load_reference()
+    return _NS
 
 
 def reference_args(ns, size=320, max_len=20, negs=3, batch=48):

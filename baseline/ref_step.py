@@ -33,14 +33,11 @@ class _NullWriter:
 
 def load(size=320, max_len=20, negs=3, batch=48, epochs=15):
     """-> (ns, args): reference namespace (TRIS, clip, train_stage1 / validate modules) + its argparse Namespace."""
-    ns = ref_loader.load_reference()
+    ns = ref_loader.load_reference_once()
     args = ref_loader.reference_args(ns, size, max_len, negs, batch)
     args.epoch = epochs
-    import train_stage1 as T  # noqa: E402  (the reference's module, imported from REF_ROOT)
-    import validate as V  # noqa: E402
-    T.writer = _NullWriter()
-    T.logger = logging.getLogger("tris_reference")
-    ns.T, ns.V = T, V
+    ns.T.writer = _NullWriter()
+    ns.T.logger = logging.getLogger("tris_reference")
     return ns, args
 
 
@@ -60,8 +57,7 @@ def build_models(ns, args, device="cpu", aux_half=None, seed=0):
     if aux_half is None:
         aux_half = dev.type == "cuda"
     if aux_half:
-        from CLIP.clip.model import convert_weights
-        convert_weights(aux)
+        ns.convert_weights(aux)
     return model, aux
 
 

@@ -332,10 +332,10 @@ def run_gpu_arm(a):
         gemm_calls = []
         orig = L.gemm_raw
 
-        def timed_gemm(desc):
+        def timed_gemm(desc, launches=1):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            orig(desc)
+            orig(desc, launches)
             e.record()
             taps = desc.taps if (desc.wgrad and desc.taps > 1) else 1
             nb = max(1, desc.batch)

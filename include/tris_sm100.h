@@ -53,9 +53,9 @@ typedef struct tris_gemm_desc {
     void* d;              /* bf16 or f32, row-major [M, ldd] (conv: NHWC pixels x channels) */
     const float* bias;    /* [N] or NULL (added before activation) */
     const void* residual; /* bf16 [M, ldd] or NULL (added after activation) */
-    float* stats;         /* [2N] column sum / sum of squares of the stored (bf16-rounded) output, accumulated per CTA
-                             in shared memory and flushed with one atomic per column (BatchNorm batch statistics,
-                             model.py:18-28) or NULL */
+    float* stats;         /* [stats_parts][2N] or NULL: per-CTA partial column statistics of the stored (bf16-rounded)
+                             output -- row r is written by CTA r with plain stores (rows beyond the grid are cleared), so
+                             the consumer's in-order sum is bit-reproducible (BatchNorm batch statistics, model.py:18-28) */
     int32_t a_mode, b_mode;
     int32_t M, N, K;      /* GEMM extents.  conv fwd/dgrad: M = n*h*w pixels, K = taps*channels(A).
                              conv wgrad: M = channels(A), N = channels(B), K = n*h*w pixels (per tap) */
@@ -68,22 +68,45 @@ typedef struct tris_gemm_desc {
     int32_t wgrad;        /* 1 = conv weight-gradient form */
     int32_t b_tap_stride; /* MN2D B of a conv dgrad: element offset between taps along the contiguous dim */
     int32_t block_n;      /* 32..256, multiple of 32 (UMMA N) */
-    int32_t split_k;      /* >=1; >1 requires out f32 + atomic */
+    int32_t split_k;      /* >=1; >1 requires out f32 and `splitk_ws`: the partials of the splits are stored to the
+                             workspace and added in split order by a second kernel (bit-reproducible) */
     int32_t act;          /* TRIS_ACT_* */
     int32_t out_dtype;    /* TRIS_DT_* */
-    int32_t atomic;       /* 1 = red.add.f32 into d (d pre-zeroed by the caller) */
+    int32_t atomic;       /* 1 = accumulate into d (d += result; f32 only): TMA reduce-add of the single partial when
+                             split_k == 1, `d += sum of partials` in the split-K second stage otherwise */
     int32_t max_ctas;     /* 0 = one per SM */
     void* d_pre;          /* optional bf16 [M, ldd]: pre-activation (post-bias) values, saved for backward */
-    const void* dact_src; /* optional bf16 [M, ldd]: epilogue multiplies by act'(dact_src) instead of applying act
-                             (fuses the QuickGELU / ReLU derivative into a dgrad GEMM) */
+    const void* dact_src; /* optional bf16 [M, ldd]: epilogue computes (acc [+ residual]) * act'(dact_src) instead of
+                             act(acc) [+ residual] (fuses the QuickGELU / ReLU derivative into a dgrad GEMM) */
     int32_t batch;        /* >1: `batch` independent GEMMs of extents M,N,K (2-D modes only; per-image products of the
                              cross-modal attention, model/attn.py:118-131).  Rows beyond M / K of one batch entry are
                              zero-filled by TMA, so M and K need not be multiples of the tile */
     float scale;          /* accumulator scale applied before the bias; 0 is read as 1 (no scaling) */
     int64_t a_batch_stride, b_batch_stride, d_batch_stride; /* elements; 0 for A/B = operand shared by all batches */
+    int32_t stats_parts;  /* rows of `stats` (>= 1 when stats != NULL); the grid is capped to it */
+    int32_t stats_mode;   /* 0: (sum x, sum x^2).  1: BatchNorm-backward sums (sum g, sum g*(y - mu)) of the stored g against
+                             `stats_y` / `stats_mu` (fuses the dgamma/dbeta reduction of model.py:18-28 into the GEMM
+                             that produces the upstream gradient) */
+    const void* stats_y;  /* bf16, same shape / leading dimension as d */
+    const float* stats_mu; /* [N] */
+    const float* mask_sc; /* optional [N] with mask_sh: d *= ((stats_y * mask_sc + mask_sh) > 0), the ReLU mask of */
+    const float* mask_sh; /*   relu(bn(y)) recomputed from y (2-D and conv fwd/dgrad modes, bf16 output) */
+    float* splitk_ws;     /* fp32 workspace, >= split_k * M * W floats (W = taps*N for conv wgrad, N rounded up to 4 else) */
+    int32_t defer_reduce; /* 1 = split-K: only store the partials; the caller reduces them later, many tensors per launch, with
+                             tris_splitk_reduce_multi (rows = M, w = W, split = the effective split this call reports back) */
+    int32_t split_used;   /* OUT: effective split count of this call (<= split_k) */
 } tris_gemm_desc;
 
-int tris_gemm(const tris_gemm_desc* desc, tris_stream_t stream);
+int tris_gemm(tris_gemm_desc* desc, tris_stream_t stream);
+
+/* Second stage of deferred split-K weight gradients: d[m*ldd + j] (+)= sum_s ws[(s*rows + m)*w + j], s in order. */
+#define TRIS_REDUCE_MAX 64
+typedef struct tris_reduce_item {
+    const float* ws;
+    float* d;
+    int32_t rows, w, ldd, split, accumulate, pad_;
+} tris_reduce_item;
+int tris_splitk_reduce_multi(const tris_reduce_item* items, int n, tris_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Non-GEMM kernels.  Same conventions as above.  `void*` activation buffers are bf16 unless stated; NHWC for
@@ -91,18 +114,25 @@ int tris_gemm(const tris_gemm_desc* desc, tris_stream_t stream);
  * Each entry names the reference arithmetic it replaces (paths relative to fawnliu/TRIS). */
 
 /* ---- bn_act.cu */
-/* nn.BatchNorm2d (train: batch statistics from the GEMM epilogue sums + running-stat update; eval: running stats) + ReLU
- * + AvgPool2d(pool) + residual add / second BN branch (downsample) -- CLIP/clip/model.py:18-28,36-40,42-55. */
+/* nn.BatchNorm2d (train: batch statistics = in-order sum of the GEMM epilogue's partial rows stats[stats_parts][2C] in a
+ * finalize kernel + running-stat update; eval: running stats) + ReLU + AvgPool2d(pool) + residual add / second BN branch
+ * (downsample) -- CLIP/clip/model.py:18-28,36-40,42-55.  fold_half = c/2: channels c and c + c/2 are one BatchNorm channel
+ * (image-pair-packed stem).  save_scale0 / save_shift0 (optional, [C]): gamma*invstd and beta - mean*gamma*invstd of branch 0,
+ * kept for the backward GEMM epilogues that recompute the ReLU mask from y. */
 int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, const float* beta0, float* rm0,
     float* rv0, float* save_mean0, float* save_invstd0, const void* y1, const float* stats1, const float* gamma1,
     const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1, const void* residual, void*
-    out, int n, int h, int w, int c, int pool, int relu, int train, float momentum, float eps, tris_stream_t
-    stream);
-/* backward of the above: per-channel reductions (dgamma, dbeta) then dy (and the residual gradient g_out) -- model.py:42-55. */
+    out, int n, int h, int w, int c, int pool, int relu, int train, float momentum, float eps, int stats_parts,
+    int fold_half, float* save_scale0, float* save_shift0, tris_stream_t stream);
+/* backward of the above: per-channel reductions (two-stage, fixed order: partial rows in `ws`, then a finalize kernel
+ * that also adds into dgamma / dbeta) then dy (and the residual gradient g_out) -- model.py:42-55.  ws holds
+ * [nparts][K][C] partial rows + [K][C] finalized sums (K = 3 with a second branch, else 2); ext_parts > 0: the rows were
+ * written by the GEMM that produced `dout` (tris_gemm stats_mode 1) and `dout` is already the masked gradient. */
 int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* gamma0, const float* beta0, const
     float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0, const void* y1, const
     float* gamma1, const float* beta1, const float* save_mean1, const float* save_invstd1, float* dgamma1, float*
-    dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, int fold_half, tris_stream_t stream);
+    dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, int fold_half, float* ws,
+    long ws_floats, int ext_parts, tris_stream_t stream);
 /* nn.AvgPool2d(2) on NHWC bf16 (the anti-aliased stride of the downsample branch, model.py:37). */
 int tris_avgpool2_fwd(const void* x, void* out, int n, int h, int w, int c, tris_stream_t stream);
 /* its adjoint (+ optional accumulate source). */
@@ -156,12 +186,11 @@ int tris_stage1_loss_bwd(const void* f, const void* g, const float* cls, const f
 /* ---- misc.cu */
 /* data movement of the stride-2 3x3 stem conv on the fp32 NCHW image (model.py:212-217,255-258). */
 int tris_stem_im2col(const float* img, void* col, int n, int h, int w, tris_stream_t stream);
-/* pair-packed stem (two images per 64-channel row, block-diagonal weights): im2col of an image pair, block-diagonal weight packing /
- * gradient un-packing, and the fold of per-channel statistics of the two halves. */
+/* pair-packed stem (two images per 64-channel row, block-diagonal weights): im2col of an image pair, block-diagonal weight
+ * packing / gradient un-packing (the fold of the two halves' statistics happens in the BatchNorm finalize kernels). */
 int tris_stem_im2col_pair(const float* img, void* col, int n, int h, int w, tris_stream_t stream);
 int tris_pack_conv_blockdiag(const float* w, void* out, int co, int ci, int khw, int reps, tris_stream_t stream);
 int tris_unpack_conv_grad_blockdiag(const float* gp, float* gw, int co, int ci, int khw, int reps, tris_stream_t stream);
-int tris_fold_pairs(float* a, float* b, float* c, int half, tris_stream_t stream);
 /* fp32 master -> bf16 operand copy of all parameters. */
 int tris_f32_to_bf16(const float* src, void* dst, long n, tris_stream_t stream);
 /* OIHW fp32 -> [Cout, taps*Cin] bf16 (tap-major K) for the implicit-GEMM convs. */
@@ -182,9 +211,10 @@ int tris_l2norm_bwd(const void* dy, const void* y, const float* inv_norm, void* 
 /* nn.InstanceNorm2d(affine) [+ ReLU] [+ 0.1-residual mix] (attn.py:72-86,102-105; model_stage1.py:73). */
 int tris_instnorm_fwd(const void* x, const float* gamma, const float* beta, const void* mix_add, void* out, float*
     mean, float* invstd, int batch, int P, int C, float mix_scale, int relu, float eps, tris_stream_t stream);
-/* its backward (dgamma / dbeta accumulated). */
+/* its backward.  ws (optional): fp32 [2][batch][C] per-image partial rows of dgamma (plane 0) / dbeta (plane 1), plain
+ * stores -- add the rows in order with tris_splitk_reduce_multi (split = batch). */
 int tris_instnorm_bwd(const void* dout, const void* x, const float* gamma, const float* beta, const float* mean,
-    const float* invstd, void* dx, float* dgamma, float* dbeta, int batch, int P, int C, float mix_scale, int relu,
+    const float* invstd, void* dx, float* ws, int batch, int P, int C, float mix_scale, int relu,
     tris_stream_t stream);
 /* y = a*x + b*y on bf16. */
 int tris_axpby(const void* x, void* y, float a, float b, long n, tris_stream_t stream);
@@ -200,14 +230,17 @@ int tris_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, 
 /* token_embedding[ids] + positional_embedding, EOT index = argmax(ids) (model.py:552-564). */
 int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D,
     tris_stream_t stream);
-/* scatter-add into the embedding / positional gradients. */
+/* dE[ids] += dx, dP += sum_n dx: owner-computes (first occurrence of a token id adds all its occurrences in order), no
+ * atomics. */
 int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, int L, int D, tris_stream_t stream);
 /* LayerNorm in fp32 (model.py:352-358). */
 int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int
     rows, int D, float eps, tris_stream_t stream);
-/* its backward (+ residual-gradient add, dgamma / dbeta). */
+/* its backward (+ residual-gradient add).  ws (optional): fp32 [2][ws_rows][D] per-CTA partial rows of dgamma (plane 0) /
+ * dbeta (plane 1) from exactly ws_rows CTAs (1 <= ws_rows <= ceil(rows / 8)); add them in order with
+ * tris_splitk_reduce_multi (split = ws_rows). */
 int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-    const void* add, void* dx, float* dgamma, float* dbeta, int rows, int D, tris_stream_t stream);
+    const void* add, void* dx, float* ws, int ws_rows, int rows, int D, tris_stream_t stream);
 /* softmax(q k^T / 8 [+ causal mask]) v per (sample, head), head dim 64 (nn.MultiheadAttention in model.py:366-386). */
 int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causal, tris_stream_t stream);
 /* its backward (dq, dk, dv packed like qkv). */
@@ -217,8 +250,9 @@ int tris_attn_bwd(const void* qkv, const void* dout, void* dqkv, int n, int L, i
 int tris_gather_rows(const void* x, const int* idx, void* out, int rows, int D, tris_stream_t stream);
 /* adjoint of the gather into a zero tensor. */
 int tris_scatter_rows(const void* src, const int* idx, void* out, int rows, int D, tris_stream_t stream);
-/* out[c] += sum_r x[r,c] (bias gradients). */
-int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream);
+/* ws[chunk][c] = sum over the rows of chunk `chunk` of x[r,c] (bias gradients: add the chunk rows in order with
+ * tris_splitk_reduce_multi, split = chunks). */
+int tris_colsum(const void* x, float* ws, int chunks, int rows, int N, tris_stream_t stream);
 /* class token + patch tokens + positional embedding (model.py:436-441). */
 int tris_vit_assemble(const void* patch, const float* cls, const float* pos, void* tok, int n, int T, int D,
     tris_stream_t stream);

@@ -46,10 +46,11 @@ def test_linear_fwd_epilogue(G):
     pre = x.float() @ w.float().t() + bias
     out = G.linear_fwd(x, w, bias, act=L.ACT_QUICKGELU, residual=res)
     assert rel(out, pre * torch.sigmoid(1.702 * pre) + res.float()) < 1e-2
-    stats = torch.zeros(2 * n, device="cuda")
+    stats = torch.full((148 * 2 * n,), 7.0, device="cuda")     # partial rows: every row is written by the kernel
     out = G.linear_fwd(x, w, bias, act=L.ACT_RELU)
     assert rel(out, F.relu(pre)) < 1e-2
     out = G.linear_fwd(x, w, bias, stats=stats)        # column statistics of the stored (bf16) output
+    stats = stats.view(148, 2 * n).sum(0)
     assert rel(stats[:n], pre.sum(0)) < 3e-3
     assert rel(stats[n:], (pre * pre).sum(0)) < 3e-3
     assert rel(stats[:n], out.float().sum(0)) < 1e-4
@@ -82,8 +83,9 @@ def test_conv3x3_fwd(G, n, h, w, ci, co):
     x = rnd(n, h, w, ci, seed=1)
     wt = rnd(co, ci, 3, 3, seed=2, scale=(9 * ci) ** -0.5)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
-    stats = torch.zeros(2 * co, device="cuda")
+    stats = torch.full((148 * 2 * co,), 7.0, device="cuda")
     out = G.conv3x3_fwd(x, G.pack_conv3x3(wt), stats=stats)
+    stats = stats.view(148, 2 * co).sum(0)
     assert rel(out, ref) < 1e-2
     assert rel(stats[:co], ref.sum((0, 1, 2))) < 3e-3
     assert rel(stats[co:], (ref * ref).sum((0, 1, 2))) < 3e-3
@@ -141,3 +143,78 @@ def test_strided_views_and_batched(G):
     G.gemm_ex(at, lp, dvv, P, C, T, a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, lda=104, ldb=C, batch=Bn, a_bs=T * 104, b_bs=T * C,
               d_bs=P * C)
     assert rel(dvv, torch.bmm(at[:, :, :P].float().transpose(1, 2), lp.float())) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ round 2: deterministic reductions
+def _bn_vectors(c, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mean = torch.randn(c, generator=g, device="cuda") * 0.2
+    sc = torch.rand(c, generator=g, device="cuda") + 0.5
+    sh = torch.randn(c, generator=g, device="cuda") * 0.3
+    return mean, sc, sh
+
+
+def _check_parts(parts, c, g, y, mean, tol=3e-3):
+    rows = parts[: 148 * 2 * c].view(148, 2 * c).sum(0)
+    gf, yf = g.float().reshape(-1, c), y.float().reshape(-1, c)
+    assert rel(rows[:c], gf.sum(0)) < tol
+    assert rel(rows[c:], (gf * (yf - mean)).sum(0)) < tol
+
+
+@pytest.mark.parametrize("m,n,k,mask", [(4800, 512, 256, True), (19200, 256, 1024, True), (1000, 136, 64, True), (4800, 1024, 256, False)])
+def test_dgrad_with_fused_bn_backward_sums(G, m, n, k, mask):
+    """linear_dgrad with the BatchNorm-backward epilogue: stored g = (dy W [+ r] [* relu'(x)]) * [y*sc+sh > 0] and the
+    partial rows (sum g, sum g (y - mean)) of the stored g."""
+    from tris_b200 import _lib as L
+    dy, w = rnd(m, n, seed=1), rnd(n, k, seed=2, scale=n ** -0.5)
+    y = rnd(m, k, seed=3)
+    mean, sc, sh = _bn_vectors(k, 4)
+    parts = torch.full((148 * 2 * k + 2 * k,), 3.0, device="cuda")
+    ref = dy.float() @ w.float()
+    if mask:
+        out = G.linear_dgrad(dy, w, bwd_stats=(parts, y, mean, sc, sh))
+        ref = ref * ((y.float() * sc + sh) > 0)
+    else:       # residual + ReLU derivative of a shared activation (bn3 of the block in front)
+        r, x = rnd(m, k, seed=5), rnd(m, k, seed=6)
+        out = G.linear_dgrad(dy, w, residual=r, dact_src=x, act=L.ACT_RELU, bwd_stats=(parts, y, mean, None, None))
+        ref = (ref + r.float()) * (x.float() > 0)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-2
+    _check_parts(parts, k, out, y, mean)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(3, 20, 20, 64, 64), (2, 40, 40, 128, 128), (5, 10, 10, 256, 256), (3, 12, 10, 64, 128)])
+def test_conv_dgrad_with_fused_bn_backward_sums(G, n, h, w, ci, co):
+    dy = rnd(n, h, w, co, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(9 * co) ** -0.5)
+    y = rnd(n, h, w, ci, seed=3)
+    mean, sc, sh = _bn_vectors(ci, 4)
+    parts = torch.full((148 * 2 * ci + 2 * ci,), 3.0, device="cuda")
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    ref = ref * ((y.float() * sc + sh) > 0)
+    out = G.conv3x3_dgrad(dy, G.pack_conv3x3(wt), ci, bwd_stats=(parts, y, mean, sc, sh))
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-2
+    _check_parts(parts, ci, out, y, mean)
+
+
+def test_weight_gradients_are_bit_reproducible(G):
+    """Split-K partials go through a workspace and are added in split order: two runs give identical bits (the round-1
+    kernels used arrival-order TMA reduce-adds)."""
+    dy, x = rnd(76800, 128, seed=1, scale=0.01), rnd(76800, 512, seed=2)
+    a = G.linear_wgrad(dy, x).clone()
+    for _ in range(3):
+        assert torch.equal(a, G.linear_wgrad(dy, x))
+    acc = torch.ones(128, 512, device="cuda")
+    G.linear_wgrad(dy, x, out=acc, accumulate=True)
+    assert rel(acc - 1.0, dy.float().t() @ x.float()) < 3e-3
+    xc, dyc = rnd(48, 40, 40, 128, seed=3), rnd(48, 40, 40, 128, seed=4, scale=0.01)
+    b = G.conv3x3_wgrad(dyc, xc).clone()
+    for _ in range(3):
+        assert torch.equal(b, G.conv3x3_wgrad(dyc, xc))
+    st = torch.zeros(148 * 2 * 512, device="cuda")
+    w = rnd(512, 128, seed=5)
+    o1 = G.linear_fwd(dy, w, stats=st).clone()
+    s1 = st.clone()
+    G.linear_fwd(dy, w, stats=st)
+    assert torch.equal(s1, st) and torch.equal(o1, G.linear_fwd(dy, w, stats=st))

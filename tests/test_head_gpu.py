@@ -74,8 +74,9 @@ def test_response_head_fwd_bwd(K, B, P):
     o = O.tris_head(sc, (h, h), (h * 32, h * 32), True)
     obj = (o["cls_out"] * dcls.cpu()).sum() + (o["cls_fg"] * dfg.cpu()).sum() + (o["maps10"].reshape(B, P) * dmaps.cpu()).sum()
     (gs,) = torch.autograd.grad(obj, sc)
-    dls = torch.zeros((), device="cuda")
+    dls = torch.zeros((B,), device="cuda")                    # per-image partials (added in order by the caller)
     D = K.head_bwd(R, ls, dcls, dfg, dmaps, mbar, am, dls, T, 3.0, 0.01)
+    dls = dls.sum()
     assert rel(D[:, :, :T].float() / ls.exp(), gs) < 1e-2      # D = dL/dR = e^s dL/dscore (bf16)
     assert abs(dls.item() - (gs * sc.detach()).sum().item()) < 2e-2 * (gs * sc.detach()).abs().sum().item()
 

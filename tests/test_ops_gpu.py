@@ -48,9 +48,13 @@ def make_bn(K, c, seed):
     return K.BNState(u(0.5, 1.5), u(-0.3, 0.3), u(-0.1, 0.1), u(0.5, 1.5), torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"))
 
 
-def stats_of(y):
+def stats_of(y, parts=148):
+    """Partial-statistics rows [parts, 2C] as the GEMM epilogue writes them: the rows are split over the parts."""
     f = y.float().reshape(-1, y.shape[-1])
-    return torch.cat([f.sum(0), (f * f).sum(0)])
+    rows = torch.zeros((parts, 2 * f.shape[1]), device=y.device)
+    for i, chunk in enumerate(f.tensor_split(min(parts, 7))):
+        rows[i] = torch.cat([chunk.sum(0), (chunk * chunk).sum(0)])
+    return rows.reshape(-1).contiguous()
 
 
 @pytest.mark.parametrize("c,pool,mode", [(64, 1, "plain"), (256, 2, "plain"), (512, 1, "residual"), (2048, 1, "dual"), (32, 1, "plain")])
@@ -350,8 +354,8 @@ def test_bottleneck_block_fwd_bwd_vs_oracle(tris, name, hw):
     tower.stats_buf.zero_()
 
     def stats(c):
-        s = tower.stats_buf[so[0]: so[0] + 2 * c]
-        so[0] += 2 * c
+        s = tower.stats_buf[so[0]: so[0] + 2 * c * 148]
+        so[0] += 2 * c * 148
         return s
 
     sdb = {k: v.clone() for k, v in m.state_dict().items() if k.startswith(blk.p)}
@@ -365,7 +369,7 @@ def test_bottleneck_block_fwd_bwd_vs_oracle(tris, name, hw):
     assert rel(out, nhwc(ref)) < 2e-2
     dout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3))
     eng.store.zero_grad()
-    dx = tower._block_bwd(blk, rec, nhwc(dout).contiguous().cuda().to(bf16))
+    dx, _ = tower._block_bwd(blk, rec, nhwc(dout).contiguous().cuda().to(bf16))
     gr = torch.autograd.grad(ref, [xr] + [leaf[k] for k in keys], dout)
     # Frobenius error: ReLU masks are recomputed from bf16-rounded pre-activations, so ~0.4 % of the mask bits differ
     # from the fp32 reference and each flip is an O(1) outlier in max-norm; a wrong formula shows up as >= 30 %.
@@ -400,8 +404,8 @@ def test_pair_packed_stem_matches_padded_stem(tris):
         off = [0]
 
         def stats(c):
-            s_ = rn.stats_buf[off[0]: off[0] + 2 * c]
-            off[0] += 2 * c
+            s_ = rn.stats_buf[off[0]: off[0] + 2 * c * 148]
+            off[0] += 2 * c * 148
             return s_
         x, rec = (rn._stem_fwd_pair if pair else rn._stem_fwd_padded)(img, True, stats)
         rn._stem_bwd((pair,) + rec, dx.clone())
@@ -417,3 +421,39 @@ def test_pair_packed_stem_matches_padded_stem(tris):
         assert e < 3e-2, (k, e)
     for k, v in res[True][2].items():
         assert rel(v, res[False][2][k]) < 2e-3, k
+
+
+def test_fused_bn_backward_matches_unfused_and_is_bit_reproducible(tris):
+    """RN50 tower backward with the BatchNorm-backward reductions fused into the GEMM epilogues (default) against the
+    stand-alone reduction kernels on the same tape; and two runs of the default path give identical gradient bits
+    (fixed-order two-stage reductions everywhere: no floating-point atomics in the image tower)."""
+    import tris_b200.resnet as R
+    m, eng, sd = tris
+    rn = eng.resnet
+    img = torch.randn(4, 3, 128, 128, generator=torch.Generator().manual_seed(21)).cuda()
+    dc4 = (torch.randn(4, 4, 4, 2048, generator=torch.Generator().manual_seed(22)) * 0.05).cuda().to(bf16)
+    keys = [k for k in eng.store.trainable if k.startswith("backbone.visual.") and "attnpool" not in k]
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    res = []
+    saved = R.FUSE_BN_BWD
+    try:
+        for fuse in (True, True, False, False):
+            R.FUSE_BN_BWD = fuse
+            m.load_state_dict(sd0)
+            eng.ensure_fresh(True)
+            eng.store.zero_grad()
+            c4, tape = rn.forward(img, train=True)
+            rn.backward(tape, dc4.clone())
+            torch.cuda.synchronize()
+            res.append((c4.clone(), {k: eng.store.g(k).clone() for k in keys}))
+    finally:
+        R.FUSE_BN_BWD = saved
+        m.load_state_dict(sd0)
+    assert torch.equal(res[0][0], res[1][0])
+    for k in keys:
+        assert torch.equal(res[0][1][k], res[1][1][k]), f"{k}: gradient differs between two identical runs"
+    for k in keys:
+        assert torch.equal(res[2][1][k], res[3][1][k]), f"{k}: gradient differs between two identical (unfused) runs"
+    worst = max((frob(res[0][1][k], res[2][1][k]), k) for k in keys)
+    print("fused vs unfused BatchNorm backward, worst gradient difference:", worst)
+    assert worst[0] < 3e-2, worst

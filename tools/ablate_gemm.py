@@ -21,14 +21,14 @@ mask = os.environ.get("TRIS_GEMM_DEBUG", "0")
 res = []
 def conv(tag, n_, h, ci, co):
     x = rnd(n_, h, h, ci); wp = rnd(co, 9 * ci); dy = rnd(n_, h, h, co)
-    out = torch.empty(n_, h, h, co, device="cuda", dtype=bf16); st = torch.zeros(2 * co, device="cuda")
+    out = torch.empty(n_, h, h, co, device="cuda", dtype=bf16); st = torch.zeros(148 * 2 * co, device="cuda")
     dx = torch.empty_like(x); gw = torch.zeros(co, 9 * ci, device="cuda")
     res.append((tag + " fwd", run(lambda: G.conv3x3_fwd(x, wp, stats=st, out=out))))
     res.append((tag + " dgrad", run(lambda: G.conv3x3_dgrad(dy, wp, ci, out=dx))))
     res.append((tag + " wgrad", run(lambda: G.conv3x3_wgrad(dy, x, out=gw))))
 def lin(tag, M, ci, co):
     x, w, dy = rnd(M, ci), rnd(co, ci), rnd(M, co)
-    out = torch.empty(M, co, device="cuda", dtype=bf16); st = torch.zeros(2 * co, device="cuda")
+    out = torch.empty(M, co, device="cuda", dtype=bf16); st = torch.zeros(148 * 2 * co, device="cuda")
     dx = torch.empty(M, ci, device="cuda", dtype=bf16); gw = torch.zeros(co, ci, device="cuda")
     res.append((tag + " fwd", run(lambda: G.linear_fwd(x, w, out=out, stats=st))))
     res.append((tag + " dgrad", run(lambda: G.linear_dgrad(dy, w, out=dx))))

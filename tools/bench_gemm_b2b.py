@@ -26,7 +26,7 @@ for name, m, n, k in [("lin 307200x256x64", 307200, 256, 64), ("lin 307200x64x25
 for n_, h, ci, co in [(48, 80, 64, 64), (48, 40, 128, 128), (48, 20, 256, 256), (48, 10, 512, 512)]:
     x = rnd(n_, h, h, ci); wp = rnd(co, 9 * ci); dy = rnd(n_, h, h, co)
     out = torch.empty(n_, h, h, co, device="cuda", dtype=bf16)
-    stats = torch.zeros(2 * co, device="cuda")
+    stats = torch.zeros(148 * 2 * co, device="cuda")
     fl = 2.0 * n_ * h * h * co * 9 * ci
     run(f"conv3x3 fwd+stats {h}x{h} {ci}", lambda: G.conv3x3_fwd(x, wp, stats=stats, out=out), fl)
     dx = torch.empty_like(x)

@@ -27,12 +27,12 @@ cases = [("lin 307200x256x64 +stats", 307200, 256, 64, True), ("lin 307200x64x25
 for name, m, n, k, st in cases:
     x, w = rnd(m, k), rnd(n, k)
     out = torch.empty(m, n, device="cuda", dtype=bf16)
-    stats = torch.zeros(2 * n, device="cuda") if st else None
+    stats = torch.zeros(148 * 2 * n, device="cuda") if st else None
     run(name, lambda: G.linear_fwd(x, w, out=out, stats=stats), 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n))
 for n_, h, ci, co in [(48, 80, 64, 64), (48, 40, 128, 128), (48, 20, 256, 256), (48, 10, 512, 512)]:
     x = rnd(n_, h, h, ci); wp = rnd(co, 9 * ci); dy = rnd(n_, h, h, co)
     out = torch.empty(n_, h, h, co, device="cuda", dtype=bf16)
-    stats = torch.zeros(2 * co, device="cuda")
+    stats = torch.zeros(148 * 2 * co, device="cuda")
     fl = 2.0 * n_ * h * h * co * 9 * ci
     by = 2.0 * (x.numel() + wp.numel() + out.numel())
     run(f"conv3x3 fwd {n_}x{h}x{h} {ci}->{co}", lambda: G.conv3x3_fwd(x, wp, stats=stats, out=out), fl, by)

@@ -37,14 +37,14 @@ for name, cnt, k, ci, co, h in layers:
     ideal = max(fl / PEAK_F, by / PEAK_B) * 1e6
     if k == 1:
         x, w, dy = rnd(M, ci), rnd(co, ci), rnd(M, co)
-        out = torch.empty(M, co, device="cuda", dtype=bf16); st = torch.zeros(2 * co, device="cuda")
+        out = torch.empty(M, co, device="cuda", dtype=bf16); st = torch.zeros(148 * 2 * co, device="cuda")
         dx = torch.empty(M, ci, device="cuda", dtype=bf16); gw = torch.zeros(co, ci, device="cuda")
         tf = run(lambda: G.linear_fwd(x, w, out=out, stats=st))
         td = run(lambda: G.linear_dgrad(dy, w, out=dx))
         tw = run(lambda: G.linear_wgrad(dy, x, out=gw, accumulate=True))
     else:
         x, wp, dy = rnd(B, h, h, ci), rnd(co, 9 * ci), rnd(B, h, h, co)
-        out = torch.empty(B, h, h, co, device="cuda", dtype=bf16); st = torch.zeros(2 * co, device="cuda")
+        out = torch.empty(B, h, h, co, device="cuda", dtype=bf16); st = torch.zeros(148 * 2 * co, device="cuda")
         dx = torch.empty_like(x); gw = torch.zeros(co, 9 * ci, device="cuda")
         tf = run(lambda: G.conv3x3_fwd(x, wp, stats=st, out=out))
         td = run(lambda: G.conv3x3_dgrad(dy, wp, ci, out=dx))

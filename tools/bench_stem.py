@@ -19,7 +19,7 @@ def run(name, fn, n=10):
 for tag, n_, ci, co in [("cur  conv2/3 48x160x160 64->64", 48, 64, 64), ("pack conv2 24x160x160 64->64", 24, 64, 64), ("pack conv3 24x160x160 64->128", 24, 64, 128),
                         ("pack4 conv2 12x160x160 128->128", 12, 128, 128)]:
     x = rnd(n_, 160, 160, ci); wp = rnd(co, 9 * ci); dy = rnd(n_, 160, 160, co)
-    out = torch.empty(n_, 160, 160, co, device="cuda", dtype=bf16); st = torch.zeros(2 * co, device="cuda")
+    out = torch.empty(n_, 160, 160, co, device="cuda", dtype=bf16); st = torch.zeros(148 * 2 * co, device="cuda")
     run(tag + " fwd+stats", lambda: G.conv3x3_fwd(x, wp, stats=st, out=out))
     dx = torch.empty_like(x)
     run(tag + " dgrad", lambda: G.conv3x3_dgrad(dy, wp, ci, out=dx))

@@ -12,11 +12,11 @@ targets = []
 x, w = rnd(4800, 1024), rnd(3072, 1024); o1 = torch.empty(4800, 3072, device="cuda", dtype=bf16)
 targets.append(lambda: G.linear_fwd(x, w, out=o1))
 # layer3 1x1 conv + BN statistics  [19200,256] x [1024,256]^T
-x2, w2 = rnd(19200, 256), rnd(1024, 256); o2 = torch.empty(19200, 1024, device="cuda", dtype=bf16); st2 = torch.zeros(2048, device="cuda")
+x2, w2 = rnd(19200, 256), rnd(1024, 256); o2 = torch.empty(19200, 1024, device="cuda", dtype=bf16); st2 = torch.zeros(148 * 2048, device="cuda")
 targets.append(lambda: G.linear_fwd(x2, w2, out=o2, stats=st2))
 # layer2 3x3 conv forward / dgrad / wgrad  48x40x40x128
 xc, wc, dyc = rnd(48, 40, 40, 128), rnd(128, 9 * 128), rnd(48, 40, 40, 128)
-oc = torch.empty_like(xc); stc = torch.zeros(256, device="cuda"); gwc = torch.zeros(128, 9 * 128, device="cuda")
+oc = torch.empty_like(xc); stc = torch.zeros(148 * 256, device="cuda"); gwc = torch.zeros(128, 9 * 128, device="cuda")
 targets.append(lambda: G.conv3x3_fwd(xc, wc, stats=stc, out=oc))
 targets.append(lambda: G.conv3x3_dgrad(dyc, wc, 128, out=oc))
 targets.append(lambda: G.conv3x3_wgrad(dyc, xc, out=gwc))
@@ -24,7 +24,9 @@ targets.append(lambda: G.conv3x3_wgrad(dyc, xc, out=gwc))
 y = rnd(48, 80, 80, 256); dout = rnd(48, 80, 80, 256); outf = torch.relu(y)
 mk = lambda: torch.rand(256, device="cuda") + 0.5
 bn = ops.BNState(mk(), mk(), mk(), mk(), torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda"))
-stats = torch.cat([y.float().reshape(-1, 256).sum(0), (y.float() ** 2).reshape(-1, 256).sum(0)])
+stats = torch.zeros(148, 512, device="cuda")
+stats[0] = torch.cat([y.float().reshape(-1, 256).sum(0), (y.float() ** 2).reshape(-1, 256).sum(0)])
+stats = stats.reshape(-1)
 targets.append(lambda: ops.bn_apply(y, stats, bn, True))
 targets.append(lambda: ops.bn_bwd(dout, outf, y, bn))
 for t in targets:

@@ -42,7 +42,7 @@ def main(args):
         ck = torch.load(args.pretrain, map_location="cpu")
         print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
     aux, _ = clip.load("ViT-B-32", device="cuda", jit=False, txt_length=args.max_query_len,
-                       allow_random_init=args.synthetic_weights)
+                       allow_random_init=getattr(args, "synthetic_weights", None))
     warnings.simplefilter("ignore")      # only now: model construction / weight loading must stay loud
     max_iter = args.steps_per_epoch * args.epoch
     trainer = Stage1Trainer(model, aux, max_iter=max_iter, lr=args.lr, lr_multi=args.lr_multi, weight_decay=args.weight_decay,

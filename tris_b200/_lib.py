@@ -33,7 +33,16 @@ class GemmDesc(C.Structure):
         ("d_pre", C.c_void_p), ("dact_src", C.c_void_p),
         ("batch", C.c_int32), ("scale", C.c_float),
         ("a_batch_stride", C.c_int64), ("b_batch_stride", C.c_int64), ("d_batch_stride", C.c_int64),
+        ("stats_parts", C.c_int32), ("stats_mode", C.c_int32),
+        ("stats_y", C.c_void_p), ("stats_mu", C.c_void_p), ("mask_sc", C.c_void_p), ("mask_sh", C.c_void_p),
+        ("splitk_ws", C.c_void_p),
+        ("defer_reduce", C.c_int32), ("split_used", C.c_int32),
     ]
+
+
+class ReduceItem(C.Structure):
+    _fields_ = [("ws", C.c_void_p), ("d", C.c_void_p), ("rows", C.c_int32), ("w", C.c_int32), ("ldd", C.c_int32),
+                ("split", C.c_int32), ("accumulate", C.c_int32), ("pad_", C.c_int32)]
 
 
 class TrisLibError(RuntimeError):
@@ -84,8 +93,8 @@ def call(name: str, *args, launches: int = 1):
     launch_count += launches
 
 
-def gemm_raw(desc: GemmDesc):
+def gemm_raw(desc: GemmDesc, launches: int = 1):
     global launch_count
     rc = lib().tris_gemm(C.byref(desc), stream_ptr())
     check(rc, "tris_gemm")
-    launch_count += 1
+    launch_count += launches

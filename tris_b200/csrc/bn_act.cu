@@ -1,6 +1,8 @@
 // BatchNorm2d (train/eval) + ReLU + residual add + 2x2 average pool on NHWC bf16 activations: forward apply,
 // backward reduction and backward apply.  HBM-bound streaming kernels: 128-bit loads/stores (8 channels per
-// thread), per-channel scale/shift staged in shared memory, fp32 math, warp/block reductions + fp32 atomics.
+// thread), per-channel scale/shift staged in shared memory, fp32 math.  All reductions are two-stage with a FIXED order
+// (per-CTA partial rows, then an in-order sum in a small finalize kernel): no floating-point atomics, results are
+// bit-reproducible run to run.
 //
 // Replaces nn.BatchNorm2d / ReLU / AvgPool2d / "out += identity" of CLIP/clip/model.py:18-55, :212-232, :255-260.
 // Batch statistics (sum, sum of squares) arrive from the conv GEMM epilogue (gemm_sm100.cu).
@@ -13,6 +15,29 @@
 namespace {
 
 constexpr int kThreads = 256;
+
+// Programmatic dependent launch: the tiny finalize kernels and the apply kernels behind them are launched while their
+// predecessor still runs (launch latency hidden); griddepcontrol.wait blocks until the predecessor grid has completed and
+// its writes are visible.  Measured on the full step: 18.79 ms with, 18.82 ms without -- no gain, so it is OFF unless
+// TRIS_PDL=1 (the griddepcontrol instructions are no-ops for normally launched grids).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TRIS_PDL"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
+}
+template <class P>
+cudaError_t launch_dep(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const P& params) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
+}
 
 struct Vec8 {
     float v[8];
@@ -57,30 +82,108 @@ struct ApplyParams {
     float count, momentum, eps;
 };
 
+struct FinalizeParams;
 __device__ __forceinline__ void bn_prologue(const BnBranch& b, const ApplyParams& p, float* s_scale, float* s_shift) {
     for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
-        float mean, var;
-        if (p.train) {
-            mean = b.stats[c] / p.count;
-            var = fmaxf(b.stats[p.c + c] / p.count - mean * mean, 0.f);
-        } else {
-            mean = b.running_mean[c];
-            var = b.running_var[c];
-        }
-        const float invstd = rsqrtf(var + p.eps);
+        // train: batch mean / invstd were finalized by bn_fwd_finalize_kernel (fixed-order sum of the GEMM's partial rows)
+        const float mean = p.train ? __ldcg(b.save_mean + c) : b.running_mean[c];
+        const float invstd = p.train ? __ldcg(b.save_invstd + c) : rsqrtf(b.running_var[c] + p.eps);
         const float sc = b.gamma[c] * invstd;
         s_scale[c] = sc;
         s_shift[c] = b.beta[c] - mean * sc;
-        if (p.train && blockIdx.x == 0) {
-            b.save_mean[c] = mean;
-            b.save_invstd[c] = invstd;
-            if (b.running_mean != nullptr) {
-                const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
-                b.running_mean[c] = (1.f - p.momentum) * b.running_mean[c] + p.momentum * mean;
-                b.running_var[c] = (1.f - p.momentum) * b.running_var[c] + p.momentum * unbiased;
-            }
-        }
     }
+}
+
+
+// In-order sum of the per-CTA partial rows parts[nparts][2C] = (sum x | sum x^2) -> batch mean / invstd (+ running stats,
+// momentum update with the unbiased variance: nn.BatchNorm2d, CLIP/clip/model.py:18-28).  fold_half > 0: channels c and
+// c + fold_half are ONE BatchNorm channel (image-pair-packed stem): their sums are averaged, so that sum / count (count =
+// pixels of B/2 images) is the full-batch mean.  blockIdx.y selects the branch.
+struct FinalizeParams {
+    const float* parts[2];
+    float* rm[2]; float* rv[2]; float* mean[2]; float* invstd[2];
+    const float* gamma[2]; const float* beta[2];
+    float* scale[2]; float* shift[2];     // optional: gamma * invstd and beta - mean * gamma * invstd (recomputed-mask epilogues)
+    int nparts, c, fold_half;
+    float count, momentum, eps;
+};
+// Fixed-order sum over the rows of a partial buffer, cooperative: a CTA of 32 x G threads owns 32 consecutive columns
+// (threadIdx.x & 31) and G row groups (threadIdx.x >> 5); group g adds rows g, g + G, ... in order, the G group sums are
+// then added in order through shared memory.  The order never depends on timing -> bit-reproducible.
+constexpr int kFinGroups = 32;     // 148 partial rows / 32 groups: <= 5 loads per thread, one round trip
+constexpr int kFinGroupsBwd = 32;  // up to 592 partial rows of the stand-alone reduction kernel
+template <int G>
+__device__ __forceinline__ float fin_partial(const float* base, int nrows, long row_stride) {
+    // up to ten independent loads in flight per thread, then added in row order (rows past the end contribute an exact +0)
+    float s = 0.f;
+    constexpr int U = 10;      // 592 rows / 32 groups = 18.5 loads per thread: two batches
+    for (int r0 = threadIdx.x >> 5; r0 < nrows; r0 += U * G) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = r0 + u * G;
+            v[u] = r < nrows ? __ldg(base + r * row_stride) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += v[u];
+    }
+    return s;
+}
+template <int G>
+__device__ __forceinline__ float fin_combine(float (*sm)[33], float v) {
+    __syncthreads();
+    sm[threadIdx.x >> 5][threadIdx.x & 31] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) t += sm[g][threadIdx.x & 31];
+    return t;
+}
+
+__device__ void bn_fwd_finalize_group(const FinalizeParams& p, int br, int group, float (*sm)[33]) {
+    const int c = group * 32 + (threadIdx.x & 31);
+    const int cc = c < p.c ? c : p.c - 1;                       // tail lanes shadow a valid column (no divergence at the barriers)
+    const long rs = 2L * p.c;
+    const float* parts = p.parts[br];
+    float s, q;
+    if (p.fold_half > 0) {
+        const int lo = cc < p.fold_half ? cc : cc - p.fold_half, hi = lo + p.fold_half;
+        const float ps0 = fin_partial<kFinGroups>(parts + lo, p.nparts, rs), ps1 = fin_partial<kFinGroups>(parts + hi, p.nparts, rs);
+        const float pq0 = fin_partial<kFinGroups>(parts + p.c + lo, p.nparts, rs), pq1 = fin_partial<kFinGroups>(parts + p.c + hi, p.nparts, rs);
+        const float s0 = fin_combine<kFinGroups>(sm, ps0), s1 = fin_combine<kFinGroups>(sm, ps1);
+        const float q0 = fin_combine<kFinGroups>(sm, pq0), q1 = fin_combine<kFinGroups>(sm, pq1);
+        s = (s0 + s1) * 0.5f;
+        q = (q0 + q1) * 0.5f;
+    } else {
+        const float ps = fin_partial<kFinGroups>(parts + cc, p.nparts, rs), pq = fin_partial<kFinGroups>(parts + p.c + cc, p.nparts, rs);
+        s = fin_combine<kFinGroups>(sm, ps);
+        q = fin_combine<kFinGroups>(sm, pq);
+    }
+    if (c >= p.c || threadIdx.x >= 32) return;
+    const float mean = s / p.count;
+    const float var = fmaxf(q / p.count - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + p.eps);
+    p.mean[br][c] = mean;
+    p.invstd[br][c] = invstd;
+    if (p.scale[br] != nullptr) {
+        const float sc = p.gamma[br][c] * invstd;
+        p.scale[br][c] = sc;
+        p.shift[br][c] = p.beta[br][c] - mean * sc;
+    }
+    if (p.rm[br] != nullptr) {
+        const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
+        p.rm[br][c] = (1.f - p.momentum) * p.rm[br][c] + p.momentum * mean;
+        p.rv[br][c] = (1.f - p.momentum) * p.rv[br][c] + p.momentum * unbiased;
+    }
+}
+
+// (Folding this step into the head of the apply kernel behind an in-kernel counter was measured SLOWER, 20.0 vs 19.0 ms per
+// step: every CTA of the apply grid then pays same-address atomics for the ticket / exit protocol.  It stays a tiny kernel.)
+__global__ void __launch_bounds__(32 * kFinGroups) bn_fwd_finalize_kernel(const FinalizeParams p) {
+    __shared__ float sm[kFinGroups][33];
+    pdl_wait();                    // the conv GEMM that wrote the partial rows
+    pdl_launch_dependents();       // the apply kernel may be set up now (it waits for this grid itself)
+    bn_fwd_finalize_group(p, blockIdx.y, blockIdx.x, sm);
 }
 
 __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParams p) {
@@ -90,6 +193,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
     float* sc1 = sm + 2 * p.c;
     float* sh1 = sm + 3 * p.c;
     const bool dual = p.b1.y != nullptr;
+    if (p.train) pdl_wait();       // the finalize kernel (and, through it, the conv GEMM)
     bn_prologue(p.b0, p, sc0, sh0);
     if (dual) bn_prologue(p.b1, p, sc1, sh1);
     __syncthreads();
@@ -157,7 +261,10 @@ struct BwdParams {
     const __nv_bfloat16* dout;   // [M_out, C]
     const __nv_bfloat16* out;    // [M_out, C] forward output (relu mask source) or nullptr -> recompute from y0
     BnBranch b0, b1;             // y, gamma, beta, save_mean, save_invstd are inputs here
-    float* dgamma0; float* dbeta0; float* dgamma1; float* dbeta1;   // [C] fp32, atomically accumulated
+    float* dgamma0; float* dbeta0; float* dgamma1; float* dbeta1;   // [C] fp32 gradient buffers (+= by the finalize kernel)
+    float* parts;                // [nparts][K][C] per-CTA partial sums: k = 0 sum g, 1 sum g (y0 - mu0), 2 sum g (y1 - mu1)
+    float* red;                  // [K][C] finalized: dbeta, dgamma0, dgamma1 -- what the apply kernel reads
+    int nparts, kred, fold_half;
     __nv_bfloat16* dy0; __nv_bfloat16* dy1;   // [M_in, C]
     __nv_bfloat16* g_out;        // optional [M_out, C]: masked upstream gradient (identity branch)
     int n, h, w, c, pool, relu;
@@ -213,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdPar
     float* s_mu0 = sm + 2 * p.c;
     float* s_mu1 = sm + 3 * p.c;
     float* red = sm + 4 * p.c;   // [kThreads * 8]
+    pdl_launch_dependents();     // the finalize kernel may be set up while this grid runs
     for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
         const float invstd = p.b0.save_invstd[c], mean = p.b0.save_mean[c];
         const float sc = p.b0.gamma[c] * invstd;
@@ -247,9 +355,11 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdPar
             for (int i = 0; i < 8; ++i) dg1[i] = fmaf(g.v[i], y1.v[i] - mu1.v[i], dg1[i]);
         }
     }
-    // block reduction over the kThreads/vecs threads that share a channel group
+    // block reduction over the kThreads/vecs threads that share a channel group; the CTA's totals become row blockIdx.x of
+    // parts[nparts][K][C] (plain stores -- the finalize kernel adds the rows in order)
     const int per = kThreads / vecs;   // threads per channel group (>= 1)
-    auto block_sum = [&](float (&x)[8], float* dst, const float* scale) {
+    float* row = p.parts + static_cast<long>(blockIdx.x) * p.kred * p.c;
+    auto block_sum = [&](float (&x)[8], float* dst) {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = x[i];
@@ -258,15 +368,51 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdPar
             const int g = c >> 3, i = c & 7;
             float s = 0.f;
             for (int k = 0; k < per; ++k) s += red[(g + k * vecs) * 8 + i];
-            atomicAdd(dst + c, scale != nullptr ? s * scale[c] : s);
+            dst[c] = s;
         }
     };
-    block_sum(db, p.dbeta0, nullptr);
-    block_sum(dg0, p.dgamma0, p.b0.save_invstd);
-    if (DUAL) {
-        block_sum(db, p.dbeta1, nullptr);
-        block_sum(dg1, p.dgamma1, p.b1.save_invstd);
+    block_sum(db, row);
+    block_sum(dg0, row + p.c);
+    if (DUAL) block_sum(dg1, row + 2 * p.c);
+}
+
+// In-order sum of parts[nparts][K][C] -> red[K][C] = (dbeta, dgamma0, dgamma1) and the parameter gradients (+=), for one group
+// of 32 channels (one CTA of bn_bwd_finalize_kernel).
+__device__ void bn_bwd_finalize_group(const BwdParams& p, int group, float (*sm)[33]) {
+    const int c = group * 32 + (threadIdx.x & 31);
+    const int cc = c < p.c ? c : p.c - 1;
+    const long rs = static_cast<long>(p.kred) * p.c;
+    float part[3][2];
+    for (int k = 0; k < p.kred; ++k) {       // all loads first (independent), the barriers of the combines afterwards
+        const float* base = p.parts + static_cast<long>(k) * p.c;
+        if (p.fold_half > 0) {
+            const int lo = cc < p.fold_half ? cc : cc - p.fold_half;
+            part[k][0] = fin_partial<kFinGroupsBwd>(base + lo, p.nparts, rs);
+            part[k][1] = fin_partial<kFinGroupsBwd>(base + lo + p.fold_half, p.nparts, rs);
+        } else {
+            part[k][0] = fin_partial<kFinGroupsBwd>(base + cc, p.nparts, rs);
+            part[k][1] = 0.f;
+        }
     }
+    for (int k = 0; k < p.kred; ++k) {
+        float s = fin_combine<kFinGroupsBwd>(sm, part[k][0]);
+        if (p.fold_half > 0)     // pair-packed stem: channels c and c + fold_half are one BatchNorm channel (averaged)
+            s = (s + fin_combine<kFinGroupsBwd>(sm, part[k][1])) * 0.5f;
+        if (c >= p.c || threadIdx.x >= 32) continue;
+        if (k == 1) s *= p.b0.save_invstd[c];
+        if (k == 2) s *= p.b1.save_invstd[c];
+        p.red[k * p.c + c] = s;
+        if (k == 0) { p.dbeta0[c] += s; if (p.kred == 3) p.dbeta1[c] += s; }
+        if (k == 1) p.dgamma0[c] += s;
+        if (k == 2) p.dgamma1[c] += s;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kFinGroupsBwd) bn_bwd_finalize_kernel(const BwdParams p) {
+    __shared__ float sm[kFinGroupsBwd][33];
+    pdl_wait();
+    pdl_launch_dependents();
+    bn_bwd_finalize_group(p, blockIdx.x, sm);
 }
 
 // dy = a g + b y + c per channel with  a = gamma*invstd,  b = -a*invstd*dgamma/N,  c = a*(invstd*dgamma/N*mean - dbeta/N).
@@ -282,16 +428,17 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_apply_kernel(const BwdPara
     float* s_b1 = sm + 5 * p.c;
     float* s_c1 = sm + 6 * p.c;
     const float inv_count = 1.f / p.count;
+    pdl_wait();                    // the finalize kernel
     for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
         const float invstd = p.b0.save_invstd[c], mean = p.b0.save_mean[c];
         const float sc = p.b0.gamma[c] * invstd;
-        const float k = p.dgamma0[c] * inv_count * invstd, m = p.dbeta0[c] * inv_count;
+        const float k = __ldcg(p.red + p.c + c) * inv_count * invstd, m = __ldcg(p.red + c) * inv_count;
         s_sc[c] = sc; s_sh[c] = p.b0.beta[c] - mean * sc;
         s_b0[c] = -sc * k; s_c0[c] = sc * (k * mean - m);
         if (DUAL) {
             const float is1 = p.b1.save_invstd[c], mu1 = p.b1.save_mean[c];
             const float a1 = p.b1.gamma[c] * is1;
-            const float k1 = p.dgamma1[c] * inv_count * is1, m1 = p.dbeta1[c] * inv_count;
+            const float k1 = __ldcg(p.red + 2 * p.c + c) * inv_count * is1, m1 = __ldcg(p.red + c) * inv_count;
             s_a1[c] = a1; s_b1[c] = -a1 * k1; s_c1[c] = a1 * (k1 * mu1 - m1);
         }
     }
@@ -397,10 +544,14 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
                       float* save_mean0, float* save_invstd0, const void* y1, const float* stats1, const float* gamma1,
                       const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1,
                       const void* residual, void* out, int n, int h, int w, int c, int pool, int relu, int train,
-                      float momentum, float eps, tris_stream_t stream) {
+                      float momentum, float eps, int stats_parts, int fold_half, float* save_scale0, float* save_shift0,
+                      tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_apply_fwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pool must be 1 or 2");
     if (pool == 2 && (y1 || residual || (h & 1) || (w & 1))) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pooled form is single-branch, even h/w");
+    if (train && (stats_parts < 1 || !stats0 || (y1 && !stats1)))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: train mode needs the partial statistics rows");
+    if (fold_half < 0 || (fold_half > 0 && 2 * fold_half != c)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: fold_half must be c/2");
     ApplyParams p{};
     p.b0 = {reinterpret_cast<const __nv_bfloat16*>(y0), stats0, gamma0, beta0, rm0, rv0, save_mean0, save_invstd0};
     p.b1 = {reinterpret_cast<const __nv_bfloat16*>(y1), stats1, gamma1, beta1, rm1, rv1, save_mean1, save_invstd1};
@@ -409,20 +560,44 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
     p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = relu; p.train = train;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     p.momentum = momentum; p.eps = eps;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    FinalizeParams f{};
+    if (train) {
+        f.parts[0] = stats0; f.parts[1] = stats1;
+        f.rm[0] = rm0; f.rv[0] = rv0; f.mean[0] = save_mean0; f.invstd[0] = save_invstd0;
+        f.rm[1] = rm1; f.rv[1] = rv1; f.mean[1] = save_mean1; f.invstd[1] = save_invstd1;
+        f.gamma[0] = gamma0; f.beta[0] = beta0; f.gamma[1] = gamma1; f.beta[1] = beta1;
+        f.scale[0] = save_scale0; f.shift[0] = save_shift0; f.scale[1] = nullptr; f.shift[1] = nullptr;
+        f.nparts = stats_parts; f.c = c; f.fold_half = fold_half;
+        f.count = p.count; f.momentum = momentum; f.eps = eps;
+        TRIS_CUDA_OK(launch_dep(bn_fwd_finalize_kernel, dim3((c + 31) / 32, y1 ? 2 : 1), dim3(32 * kFinGroups), 0, s, f));
+    }
     const long total = static_cast<long>(n) * (h / pool) * (w / pool) * (c / 8);
-    bn_apply_fwd_kernel<<<grid_for(total), kThreads, 4 * c * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    TRIS_LAUNCH_OK("bn_apply_fwd_kernel");
+    if (train) {
+        TRIS_CUDA_OK(launch_dep(bn_apply_fwd_kernel, dim3(grid_for(total)), dim3(kThreads), 4 * c * sizeof(float), s, p));
+    } else {
+        bn_apply_fwd_kernel<<<grid_for(total), kThreads, 4 * c * sizeof(float), s>>>(p);
+        TRIS_LAUNCH_OK("bn_apply_fwd_kernel");
+    }
     return TRIS_OK;
 }
 
-/* Launches the reduction (dgamma/dbeta, atomically accumulated into pre-zeroed buffers) and the apply kernel. */
+/* Backward: [reduction kernel ->] finalize (in-order sum of the partial rows, += into dgamma / dbeta) -> apply.
+ * ws: fp32 workspace [nparts][K][C] partial rows followed by [K][C] finalized sums (K = 3 with a second branch, else 2).
+ * ext_parts > 0: the partial rows (K = 2: sum g | sum g (y - mean)) were already produced by the epilogue of the GEMM
+ * that computed `dout` (tris_gemm stats_mode 1, dout = masked gradient g): the reduction kernel is skipped and `dout` is
+ * used as g without a ReLU mask. */
 int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* gamma0, const float* beta0,
                 const float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0,
                 const void* y1, const float* gamma1, const float* beta1, const float* save_mean1,
                 const float* save_invstd1, float* dgamma1, float* dbeta1, void* dy1, void* g_out, int n, int h, int w,
-                int c, int pool, int relu, int fold_half, tris_stream_t stream) {
+                int c, int pool, int relu, int fold_half, float* ws, long ws_floats, int ext_parts,
+                tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_bwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: pool must be 1 or 2");
+    if (!ws) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: workspace required");
+    if (fold_half < 0 || (fold_half > 0 && 2 * fold_half != c)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: fold_half must be c/2");
+    if (ext_parts > 0 && (y1 || pool != 1)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: external partial sums are single-branch, un-pooled");
     BwdParams p{};
     p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
     p.out = reinterpret_cast<const __nv_bfloat16*>(out);
@@ -434,13 +609,22 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     p.dy0 = reinterpret_cast<__nv_bfloat16*>(dy0);
     p.dy1 = reinterpret_cast<__nv_bfloat16*>(dy1);
     p.g_out = reinterpret_cast<__nv_bfloat16*>(g_out);
-    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = relu;
+    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = ext_parts > 0 ? 0 : relu;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
+    p.kred = y1 ? 3 : 2;
+    p.fold_half = fold_half;
     const long total = static_cast<long>(n) * h * w * (c / 8);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    // cap the reduction grid: each block ends with 2-4 * C atomics
     int rgrid = grid_for(total);
     if (rgrid > 4 * tris::sm_count()) rgrid = 4 * tris::sm_count();   // 4 resident CTAs/SM (64 registers/thread)
+    const long per_row = static_cast<long>(p.kred) * c;
+    if (ext_parts > 0) {
+        rgrid = ext_parts;
+    } else if ((rgrid + 1) * per_row > ws_floats) {
+        rgrid = static_cast<int>(ws_floats / per_row) - 1;
+    }
+    if (rgrid < 1 || (rgrid + 1) * per_row > ws_floats) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: workspace of %ld floats is too small", ws_floats);
+    p.parts = ws; p.nparts = rgrid; p.red = ws + rgrid * per_row;
     const size_t rsmem = (4 * c + kThreads * 8) * sizeof(float), asmem = 7 * c * sizeof(float);
     static bool attr = false;
     if (!attr) {
@@ -448,15 +632,14 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
         TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
         attr = true;
     }
-    if (y1 != nullptr) bn_bwd_reduce_kernel<true><<<rgrid, kThreads, rsmem, s>>>(p);
-    else bn_bwd_reduce_kernel<false><<<rgrid, kThreads, rsmem, s>>>(p);
-    TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
-    if (fold_half > 0) {   // pair-packed stem: channels c and c + fold_half are one BatchNorm channel
-        if (int e = tris_fold_pairs(dgamma0, dbeta0, nullptr, fold_half, stream)) return e;
+    if (ext_parts == 0) {
+        if (y1 != nullptr) bn_bwd_reduce_kernel<true><<<rgrid, kThreads, rsmem, s>>>(p);
+        else bn_bwd_reduce_kernel<false><<<rgrid, kThreads, rsmem, s>>>(p);
+        TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
     }
-    if (y1 != nullptr) bn_bwd_apply_kernel<true><<<grid_for(total), kThreads, asmem, s>>>(p);
-    else bn_bwd_apply_kernel<false><<<grid_for(total), kThreads, asmem, s>>>(p);
-    TRIS_LAUNCH_OK("bn_bwd_apply_kernel");
+    TRIS_CUDA_OK(launch_dep(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinGroupsBwd), 0, s, p));
+    if (y1 != nullptr) TRIS_CUDA_OK(launch_dep(bn_bwd_apply_kernel<true>, dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
+    else TRIS_CUDA_OK(launch_dep(bn_bwd_apply_kernel<false>, dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
     return TRIS_OK;
 }
 

@@ -58,7 +58,13 @@ struct KParams {
     void* d;
     const float* bias;
     const __nv_bfloat16* residual;
-    float* stats;
+    float* stats;                    // [stats_parts][2N] per-CTA partial column statistics (plain stores, fixed order)
+    int stats_parts, stats_mode;     // mode 0: (sum x, sum x^2) of the stored tile; 1: (sum g, sum g*(y - mu)) (BatchNorm backward)
+    const __nv_bfloat16* stats_y;    // mode 1: y [M, ldd] (conv mode: NHWC with ldd channels)
+    const float* stats_mu;           // mode 1: per-column mean [N]
+    const float* mask_sc;            // optional [N]: multiply the output by ((stats_y * mask_sc + mask_sh) > 0)  (ReLU mask
+    const float* mask_sh;            //   of relu(bn(y)) recomputed from y)
+    int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
     int ldd, act, out_f32, atomic;
@@ -119,7 +125,9 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // Loader variants (compile-time, so the single-thread producer / issuer loops carry no mode branches or divisions)
 enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4 };
 
-template <int AM, int BM>
+// EPI = 1 adds the BatchNorm-backward epilogue (recomputed ReLU mask from y, sums (g, g (y - mu))): compiled separately so
+// that the common kernels do not carry its code.
+template <int AM, int BM, int EPI>
 // 96 registers/thread (no spills; 166 unconstrained): 352 x 96 = 33 K registers leave room for one 256-thread CTA of the
 // HBM-bound BatchNorm kernels next to a resident GEMM CTA, so side-stream weight gradients and the BN chain share SMs.
 #ifndef TRIS_GEMM_MAXNREG
@@ -161,6 +169,9 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
+    // a kernel launched behind this one with programmatic stream serialization (the BatchNorm finalize kernels) may be set
+    // up now; it blocks in griddepcontrol.wait until this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0 || warp == 10) {
         // ------------------------------------------------------------------ TMA producers: warp 0 feeds A, warp 10 feeds B
@@ -354,6 +365,34 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if (ncol0 + i < p.N) v[i] += __ldg(p.bias + ncol0 + i);
                 }
                 const long off = grow * p.ldd + ncol0;
+                if (EPI == 1 && p.mask_sc != nullptr) {
+                    // g = acc * [relu(bn(y)) > 0], the mask recomputed from y (one 64-byte row segment per thread)
+                    long yrow = grow;
+                    bool yok = rvalid;
+                    if (AM == LD_CONV) {
+                        int qh, qw;
+                        p.fd_tw.divmod(row, qh, qw);
+                        yok = row < p.th * p.tw && c.h0 + qh < p.img_h && c.w0 + qw < p.img_w;
+                        yrow = (static_cast<long>(c.n_i) * p.img_h + c.h0 + qh) * p.img_w + c.w0 + qw;
+                    }
+                    if (yok) {
+                        const uint4* yp = reinterpret_cast<const uint4*>(p.stats_y + yrow * p.ldd + ncol0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (ncol0 + g * 8 < p.N) {
+                                uint4 rr = __ldg(yp + g);
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 f = __bfloat1622float2(r2[j]);
+                                    const int cc = ncol0 + g * 8 + 2 * j;
+                                    if (fmaf(f.x, __ldg(p.mask_sc + cc), __ldg(p.mask_sh + cc)) <= 0.f) v[g * 8 + 2 * j] = 0.f;
+                                    if (fmaf(f.y, __ldg(p.mask_sc + cc + 1), __ldg(p.mask_sh + cc + 1)) <= 0.f) v[g * 8 + 2 * j + 1] = 0.f;
+                                }
+                            }
+                        }
+                    }
+                }
                 if (p.d_pre != nullptr && rvalid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -367,7 +406,28 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                 }
+                auto add_residual = [&]() {
+                    if (p.residual != nullptr && rvalid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (ncol0 + g * 8 < p.N) {
+                                uint4 rr = __ldg(rp + g);
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = __bfloat1622float2(r2[j]);
+                                    v[g * 8 + 2 * j] += f.x;
+                                    v[g * 8 + 2 * j + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                };
                 if (p.dact_src != nullptr) {
+                    // derivative form: d = (acc + residual) * act'(dact_src) -- the residual (the other branch of a join) is
+                    // part of the gradient that passes through the activation
+                    add_residual();
                     if (rvalid) {
                         const uint4* sp = reinterpret_cast<const uint4*>(p.dact_src + off);
 #pragma unroll
@@ -388,22 +448,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
                 }
-                if (p.residual != nullptr && rvalid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (ncol0 + g * 8 < p.N) {
-                            uint4 rr = __ldg(rp + g);
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(r2[j]);
-                                v[g * 8 + 2 * j] += f.x;
-                                v[g * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                }
+                if (p.dact_src == nullptr) add_residual();
                 // ---- stage (swizzle: 16-byte chunk index ^ (row & 7), the TMA SWIZZLE_128B pattern)
                 if (p.out_f32) {
                     const uint32_t base = stg + ch * 16384 + row * 128;
@@ -438,7 +483,10 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (AM == LD_CONV) {
                         ptx::tma_store_4d(&map_d, src, cg, c.w0, c.h0, c.n_i);
                     } else if (p.wgrad) {
-                        ptx::tma_reduce_add_3d(&map_d, src, cg, c.tap, c.m_t * kBlockM);
+                        if (p.split_ws) ptx::tma_store_4d(&map_d, src, cg, c.tap, c.m_t * kBlockM, c.split);
+                        else ptx::tma_reduce_add_3d(&map_d, src, cg, c.tap, c.m_t * kBlockM);
+                    } else if (p.split_ws) {
+                        ptx::tma_store_3d(&map_d, src, cg, c.m_t * kBlockM, c.split);
                     } else if (p.batch > 1) {
                         if (p.atomic) ptx::tma_reduce_add_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
                         else ptx::tma_store_3d(&map_d, src, cg, c.m_t * kBlockM, c.batch);
@@ -466,18 +514,40 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (conv_tile) { int qh, qw; p.fd_tw.divmod(r0, qh, qw); hh = c.h0 + qh; ww = c.w0 + qw; }
                 const uint32_t gbase = stg + (vec >> 3) * 16384;
                 const int idx = vec & 7;
+                const int scol = n0 + vec * 8;
+                float mu[8];
+                if (EPI == 1 && p.stats_mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mu[i] = scol + i < p.N ? __ldg(p.stats_mu + scol + i) : 0.f;
+                }
                 for (int r = r0; r < r1; ++r) {
                     // patch rows that overhang the image are computed (halo taps see real pixels) but never stored
                     const bool ok = !conv_tile || (hh < p.img_h && ww < p.img_w);
+                    const long yrow = conv_tile ? (static_cast<long>(c.n_i) * p.img_h + hh) * p.img_w + ww
+                                                : static_cast<long>(c.m_t) * kBlockM + r;
                     if (conv_tile && ++ww == c.w0 + p.tw) { ww = c.w0; ++hh; }
                     if (!ok) continue;
                     uint32_t w4[4];
                     ptx::ld_shared_v4(gbase + r * 128 + ((idx ^ (r & 7)) << 4), w4);
+                    if (EPI == 1 && p.stats_mode == 1) {
+                        if (scol < p.N) {
+                            const uint4 yy = __ldg(reinterpret_cast<const uint4*>(p.stats_y + yrow * p.ldd + scol));
+                            const uint32_t y4[4] = {yy.x, yy.y, yy.z, yy.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float x0 = __uint_as_float(w4[k] << 16), x1 = __uint_as_float(w4[k] & 0xffff0000u);
-                        sa[2 * k] += x0; sq[2 * k] = fmaf(x0, x0, sq[2 * k]);
-                        sa[2 * k + 1] += x1; sq[2 * k + 1] = fmaf(x1, x1, sq[2 * k + 1]);
+                            for (int k = 0; k < 4; ++k) {
+                                const float x0 = __uint_as_float(w4[k] << 16), x1 = __uint_as_float(w4[k] & 0xffff0000u);
+                                const float y0 = __uint_as_float(y4[k] << 16), y1 = __uint_as_float(y4[k] & 0xffff0000u);
+                                sa[2 * k] += x0; sq[2 * k] = fmaf(x0, y0 - mu[2 * k], sq[2 * k]);
+                                sa[2 * k + 1] += x1; sq[2 * k + 1] = fmaf(x1, y1 - mu[2 * k + 1], sq[2 * k + 1]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float x0 = __uint_as_float(w4[k] << 16), x1 = __uint_as_float(w4[k] & 0xffff0000u);
+                            sa[2 * k] += x0; sq[2 * k] = fmaf(x0, x0, sq[2 * k]);
+                            sa[2 * k + 1] += x1; sq[2 * k + 1] = fmaf(x1, x1, sq[2 * k + 1]);
+                        }
                     }
                 }
                 float* scr = s_stats + 2 * p.N;                    // [nparts][2][bn]
@@ -499,10 +569,15 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         if (ew == 0 && ptx::elect_one()) ptx::bulk_wait_all();
         if (p.stats != nullptr) {
+            // deterministic: every CTA stores its partial sums as row blockIdx.x of stats[stats_parts][2N] (tiles are
+            // assigned statically, sums inside a CTA run in a fixed order); the consumer adds the rows in order.
+            // Rows no CTA owns (grid smaller than stats_parts) are cleared here.
             ptx::named_bar_sync(1, 256);
-            for (int i = tid_e; i < 2 * p.N; i += 256) {
-                const float sv = s_stats[i];
-                if (sv != 0.f) atomicAdd(p.stats + i, sv);
+            float* dst = p.stats + static_cast<long>(blockIdx.x) * 2 * p.N;
+            for (int i = tid_e; i < 2 * p.N; i += 256) dst[i] = s_stats[i];
+            for (int r = gridDim.x + blockIdx.x; r < p.stats_parts; r += gridDim.x) {
+                float* z = p.stats + static_cast<long>(r) * 2 * p.N;
+                for (int i = tid_e; i < 2 * p.N; i += 256) z[i] = 0.f;
             }
         }
     }
@@ -516,9 +591,76 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Second stage of a split-K weight gradient: d[m, j] (+)= sum_s ws[s][m][j], the partials added in split order (deterministic;
+// replaces the arrival-order TMA reduce-adds).  ws rows are compact (`w` floats), d rows have stride ldd.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ d, int rows, int w,
+                                                             int ldd, int split, int accumulate) {
+    const long per = static_cast<long>(rows) * w;
+    const long total4 = per >> 2;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long e = i << 2;
+        const int m = static_cast<int>(e / w), j = static_cast<int>(e - static_cast<long>(m) * w);
+        float4* dp = reinterpret_cast<float4*>(d + static_cast<long>(m) * ldd + j);
+        float4 acc = accumulate ? *dp : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp0 = 0; sp0 < split; sp0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = sp0 + u < split ? __ldg(reinterpret_cast<const float4*>(ws + (sp0 + u) * per + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        *dp = acc;
+    }
+}
+
+// Multi-tensor form: one launch reduces up to TRIS_REDUCE_MAX pending split-K weight gradients (blockIdx.y = item).
+struct ReduceTable {
+    tris_reduce_item it[TRIS_REDUCE_MAX];
+};
+__global__ void __launch_bounds__(256) splitk_reduce_multi_kernel(const ReduceTable t) {
+    const tris_reduce_item& q = t.it[blockIdx.y];
+    const float* __restrict__ ws = q.ws;
+    float* __restrict__ d = q.d;
+    const long per = static_cast<long>(q.rows) * q.w;
+    const long total4 = per >> 2;
+    for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long e = i << 2;
+        const int m = static_cast<int>(e / q.w), j = static_cast<int>(e - static_cast<long>(m) * q.w);
+        float4* dp = reinterpret_cast<float4*>(d + static_cast<long>(m) * q.ldd + j);
+        float4 acc = q.accumulate ? *dp : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp0 = 0; sp0 < q.split; sp0 += 8) {       // eight partials in flight, added in split order
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = sp0 + u < q.split ? __ldg(reinterpret_cast<const float4*>(ws + (sp0 + u) * per + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        *dp = acc;
+    }
+}
+
 }  // namespace
 
-extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
+extern "C" int tris_splitk_reduce_multi(const tris_reduce_item* items, int n, tris_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n < 0 || (n > 0 && !items)) return tris::fail(TRIS_ERR_SHAPE, "tris_splitk_reduce_multi: bad item list");
+    for (int o = 0; o < n; o += TRIS_REDUCE_MAX) {
+        ReduceTable t{};
+        const int cnt = n - o < TRIS_REDUCE_MAX ? n - o : TRIS_REDUCE_MAX;
+        for (int i = 0; i < cnt; ++i) {
+            t.it[i] = items[o + i];
+            if (!t.it[i].ws || !t.it[i].d || t.it[i].w % 4 || t.it[i].ldd % 4 || t.it[i].rows <= 0 || t.it[i].split < 1)
+                return tris::fail(TRIS_ERR_SHAPE, "tris_splitk_reduce_multi: item %d malformed", o + i);
+        }
+        splitk_reduce_multi_kernel<<<dim3(32, cnt), 256, 0, stream>>>(t);
+        TRIS_LAUNCH_OK("splitk_reduce_multi_kernel");
+    }
+    return TRIS_OK;
+}
+
+extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!g || !g->a || !g->b || !g->d) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: null operand");
     if (g->M <= 0 || g->N <= 0 || g->K <= 0) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: empty extent M=%d N=%d K=%d", g->M, g->N, g->K);
@@ -533,7 +675,8 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (b_mn && bn % 64) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: MN-major B needs block_n %% 64 == 0");
     if ((g->b_mode == TRIS_OP_CONV) != wgrad) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: B conv mode only for wgrad");
     if (g->atomic && g->out_dtype != TRIS_DT_F32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: atomic needs f32 output");
-    if (g->split_k > 1 && !g->atomic) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: split_k needs atomic output");
+    if (g->split_k > 1 && (g->out_dtype != TRIS_DT_F32 || !g->splitk_ws))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: split_k needs f32 output and a splitk_ws workspace");
     if (g->residual && g->out_dtype == TRIS_DT_F32 && g->atomic) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: residual+atomic");
 
     const int batch = g->batch > 1 ? g->batch : 1;
@@ -591,6 +734,12 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (split > p.kblocks) split = p.kblocks;
     p.kb_per_split = ceil_div(p.kblocks, split);
     p.split_k = ceil_div(p.kblocks, p.kb_per_split);
+    p.split_ws = p.split_k > 1 ? 1 : 0;
+    g->split_used = p.split_k;
+    if (p.split_ws && batch > 1) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: split_k with batch > 1 is not supported");
+    // compact row width of the split-K workspace: [split][M][ws_w] fp32
+    const int ws_w = wgrad ? p.taps * g->N : (g->N + 3) / 4 * 4;
+    if (p.split_ws && (g->N % 4 || g->ldd % 4)) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: split_k needs N, ldd %% 4 == 0");
 
     const bool a_mn = (g->a_mode == TRIS_OP_MN2D) || wgrad;
     p.a_atom = p.bk * 128;
@@ -608,8 +757,15 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (conv && !wgrad && out_f32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: conv forward/dgrad output is bf16");
     if (conv && (g->residual || g->d_pre || g->dact_src || g->bias))
         return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: bias/residual/d_pre/dact epilogues are for the 2-D modes");
+    if (wgrad && (g->stats || g->mask_sc)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: no stats / mask epilogue on weight gradients");
     if (wgrad && !out_f32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: weight gradients are fp32");
     if (g->stats && (out_f32 || g->N > 2048)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stats need bf16 output, N <= 2048");
+    if (g->stats && g->stats_parts < 1) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stats need stats_parts >= 1 rows");
+    if (g->stats_mode == 1 && (!g->stats || !g->stats_y || !g->stats_mu))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stats_mode 1 needs stats, stats_y and stats_mu");
+    if ((g->mask_sc != nullptr) != (g->mask_sh != nullptr) || (g->mask_sc && (!g->stats_y || out_f32)))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: the recomputed ReLU mask needs mask_sc, mask_sh, stats_y and bf16 output");
+    if (g->mask_sc && batch > 1) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: mask epilogue is for the non-batched modes");
     p.staging_bytes = bn * (out_f32 ? 4 : 2) * 128;
     if (p.staging_bytes < 16384) p.staging_bytes = 16384;
     p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 + 16384 : 0;
@@ -638,6 +794,9 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
         if (!buf) p.dbg &= ~8;
     }
     p.d = g->d; p.bias = g->bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual); p.stats = g->stats;
+    p.stats_parts = g->stats_parts; p.stats_mode = g->stats_mode;
+    p.stats_y = reinterpret_cast<const __nv_bfloat16*>(g->stats_y); p.stats_mu = g->stats_mu;
+    p.mask_sc = g->mask_sc; p.mask_sh = g->mask_sh;
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;
@@ -700,11 +859,21 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
             uint64_t str[3] = {(uint64_t)g->ldd * 2, (uint64_t)p.img_w * g->ldd * 2, (uint64_t)p.img_h * p.img_w * g->ldd * 2};
             uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
             md = tris::tensor_map_bf16(g->d, 4, dims, str, box, 2);
+        } else if (wgrad && p.split_ws) {
+            uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)p.taps, (uint64_t)g->M, (uint64_t)p.split_k};
+            uint64_t str[3] = {(uint64_t)g->N * 4, (uint64_t)ws_w * 4, (uint64_t)g->M * ws_w * 4};
+            uint32_t box[4] = {32, 1, (uint32_t)kBlockM, 1};
+            md = tris::tensor_map_bf16(g->splitk_ws, 4, dims, str, box, 4);
         } else if (wgrad) {
             uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)p.taps, (uint64_t)g->M};
             uint64_t str[2] = {(uint64_t)g->N * 4, (uint64_t)g->ldd * 4};
             uint32_t box[3] = {32, 1, (uint32_t)kBlockM};
             md = tris::tensor_map_bf16(g->d, 3, dims, str, box, 4);
+        } else if (p.split_ws) {
+            uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)p.split_k};
+            uint64_t str[2] = {(uint64_t)ws_w * 4, (uint64_t)g->M * ws_w * 4};
+            uint32_t box[3] = {32, (uint32_t)kBlockM, 1};
+            md = tris::tensor_map_bf16(g->splitk_ws, 3, dims, str, box, 4);
         } else {
             uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)batch};
             uint64_t str[2] = {(uint64_t)g->ldd * esz, (uint64_t)g->d_batch_stride * esz};
@@ -721,24 +890,37 @@ extern "C" int tris_gemm(const tris_gemm_desc* g, tris_stream_t stream_) {
     if (wgrad) bm = LD_CONV_WG; else if (g->b_mode == TRIS_OP_MN2D) bm = (conv ? LD_MN2D_TAPS : LD_MN2D);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn = nullptr;
-    if (am == LD_K2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_K2D, LD_K2D>;
-    else if (am == LD_K2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_K2D, LD_MN2D>;
-    else if (am == LD_MN2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_MN2D>;
-    else if (am == LD_MN2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_K2D>;
-    else if (am == LD_CONV && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_CONV, LD_K2D>;
-    else if (am == LD_CONV && bm == LD_MN2D_TAPS) fn = tris_umma_gemm_kernel<LD_CONV, LD_MN2D_TAPS>;
-    else if (am == LD_CONV_WG && bm == LD_CONV_WG) fn = tris_umma_gemm_kernel<LD_CONV_WG, LD_CONV_WG>;
+    const int epi = (g->stats_mode == 1 || g->mask_sc != nullptr) ? 1 : 0;
+#define TRIS_PICK(A_, B_) (epi ? static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 1>) : static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 0>))
+    if (am == LD_K2D && bm == LD_K2D) fn = TRIS_PICK(LD_K2D, LD_K2D);
+    else if (am == LD_K2D && bm == LD_MN2D) fn = TRIS_PICK(LD_K2D, LD_MN2D);
+    else if (am == LD_MN2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_MN2D, 0>;
+    else if (am == LD_MN2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_K2D, 0>;
+    else if (am == LD_CONV && bm == LD_K2D) fn = TRIS_PICK(LD_CONV, LD_K2D);
+    else if (am == LD_CONV && bm == LD_MN2D_TAPS) fn = TRIS_PICK(LD_CONV, LD_MN2D_TAPS);
+    else if (am == LD_CONV_WG && bm == LD_CONV_WG) fn = tris_umma_gemm_kernel<LD_CONV_WG, LD_CONV_WG, 0>;
     else return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: unsupported operand mode combination a=%d b=%d", g->a_mode, g->b_mode);
-    static bool attr_set[8][8] = {};
-    if (!attr_set[am][bm]) {
+#undef TRIS_PICK
+    if (epi && (am == LD_MN2D || am == LD_CONV_WG)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: BatchNorm-backward epilogue needs a K-major / conv A operand");
+    static bool attr_set[8][8][2] = {};
+    if (!attr_set[am][bm][epi]) {
         TRIS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[am][bm] = true;
+        attr_set[am][bm][epi] = true;
     }
     const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k * p.batch;
     int ctas = tris::sm_count();
     if (g->max_ctas > 0 && g->max_ctas < ctas) ctas = g->max_ctas;
     if (total_tiles < ctas) ctas = total_tiles;
+    if (g->stats && ctas > g->stats_parts) ctas = g->stats_parts;   // one partial-statistics row per CTA
     fn<<<ctas, kThreads, smem_bytes, stream>>>(*ma, *mb, *md, p);
     TRIS_LAUNCH_OK("tris_umma_gemm_kernel");
+    if (p.split_ws && !g->defer_reduce) {
+        const long total4 = static_cast<long>(g->M) * ws_w / 4;
+        long blocks = (total4 + 255) / 256;
+        if (blocks > 2L * tris::sm_count()) blocks = 2L * tris::sm_count();
+        splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(g->splitk_ws, reinterpret_cast<float*>(g->d), g->M, ws_w, g->ldd,
+                                                                          p.split_k, g->atomic);
+        TRIS_LAUNCH_OK("splitk_reduce_kernel");
+    }
     return TRIS_OK;
 }

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
     }
 }
 
-// D bf16 [B,P,Tp] = dL/dR ; dlogit_scale += sum dz * z.
+// D bf16 [B,P,Tp] = dL/dR ; dlogit_scale[b] = per-image sum dz * z (fp32 [B]; the caller adds them in order: no atomics).
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ R, const float* __restrict__ logit_scale,
                                                        const float* __restrict__ dcls_out, const float* __restrict__ dcls_fg,
                                                        const float* __restrict__ dmaps, const float* __restrict__ mbar,
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     if (threadIdx.x == 0 && dlogit_scale != nullptr) {
         float s = 0.f;
         for (int w = 0; w < nw; ++w) s += red[w];
-        atomicAdd(dlogit_scale, s);
+        dlogit_scale[b] = s;          // per-image partial (plain store); the caller adds the B values in order
     }
 }
 

@@ -137,22 +137,6 @@ __global__ void unpack_conv_grad_blockdiag_kernel(const float* __restrict__ gp, 
         gw[i] += s;
     }
 }
-// a[c] = a[c + half] = (a[c] + a[c + half]) / 2 for c < half, on up to three arrays (statistics of channels that are the
-// same BatchNorm channel in the pair-packed layout)
-__global__ void fold_pairs_kernel(float* a, float* b, float* c3, int half) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= half) return;
-    float* arr[3] = {a, b, c3};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (arr[k] != nullptr) {
-            const float m = 0.5f * (arr[k][i] + arr[k][i + half]);
-            arr[k][i] = m;
-            arr[k][i + half] = m;
-        }
-    }
-}
-
 // OIHW fp32 [co, ci, kh, kw] -> bf16 [co_pad, kh*kw*ci_pad] with k = (r*kw+s)*ci_pad + c (zero padding)
 __global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int co, int ci, int khw, int co_pad,
                                  int ci_pad) {
@@ -280,13 +264,14 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const __nv_bfloat16* 
     if (pg == 0 && mean_out != nullptr) { mean_out[b * C + c] = mean; invstd_out[b * C + c] = invstd; }
 }
 
-// backward of out = mix_scale * act(IN(x)*gamma+beta): dx, dgamma/dbeta (atomics).  relu mask recomputed from x.
+// backward of out = mix_scale * act(IN(x)*gamma+beta): dx, and per-image partial rows of dgamma/dbeta in ws[2][B][C] (plain
+// stores; the caller's queue adds the B rows in order).  relu mask recomputed from x.
 template <int IN_MAXP>
 __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
-                                                           __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int P, int C, float mix_scale, int relu) {
+                                                           __nv_bfloat16* __restrict__ dx, float* __restrict__ ws,
+                                                           int P, int C, float mix_scale, int relu) {
     __shared__ float red[2][4][64];
     const int c = blockIdx.x * 64 + threadIdx.x, b = blockIdx.y, pg = threadIdx.y;
     const float mean = mean_in[b * C + c], invstd = invstd_in[b * C + c], g = gamma[c], be = beta[c];
@@ -307,7 +292,10 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const __nv_bfloat16* 
     __syncthreads();
     s1 = red[0][0][threadIdx.x] + red[0][1][threadIdx.x] + red[0][2][threadIdx.x] + red[0][3][threadIdx.x];
     s2 = red[1][0][threadIdx.x] + red[1][1][threadIdx.x] + red[1][2][threadIdx.x] + red[1][3][threadIdx.x];
-    if (pg == 0) { atomicAdd(dbeta + c, s1); atomicAdd(dgamma + c, s2); }
+    if (pg == 0 && ws != nullptr) {
+        ws[(static_cast<long>(gridDim.y) + b) * C + c] = s1;      // plane 1: dbeta
+        ws[static_cast<long>(b) * C + c] = s2;                     // plane 0: dgamma
+    }
     const float a = g * invstd, m1 = s1 / P, m2 = s2 / P;
     int i = 0;
     for (int p = pg; p < P; p += 4, ++i) {
@@ -370,12 +358,6 @@ int tris_unpack_conv_grad_blockdiag(const float* gp, float* gw, int co, int ci, 
     unpack_conv_grad_blockdiag_kernel<<<grid1d(static_cast<long>(co) * ci * khw), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         gp, gw, co, ci, khw, reps);
     TRIS_LAUNCH_OK("unpack_conv_grad_blockdiag_kernel");
-    return TRIS_OK;
-}
-
-int tris_fold_pairs(float* a, float* b, float* c, int half, tris_stream_t stream) {
-    fold_pairs_kernel<<<(half + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, c, half);
-    TRIS_LAUNCH_OK("fold_pairs_kernel");
     return TRIS_OK;
 }
 
@@ -442,13 +424,13 @@ int tris_instnorm_fwd(const void* x, const float* gamma, const float* beta, cons
 }
 
 int tris_instnorm_bwd(const void* dout, const void* x, const float* gamma, const float* beta, const float* mean,
-                      const float* invstd, void* dx, float* dgamma, float* dbeta, int batch, int P, int C, float mix_scale,
+                      const float* invstd, void* dx, float* ws, int batch, int P, int C, float mix_scale,
                       int relu, tris_stream_t stream) {
     if (C % 64 || P > 256) return tris::fail(TRIS_ERR_SHAPE, "tris_instnorm_bwd: C%%64, P<=256 (got C=%d P=%d)", C, P);
     auto fn = P <= 128 ? instnorm_bwd_kernel<32> : instnorm_bwd_kernel<64>;
     fn<<<dim3(C / 64, batch), dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, mean, invstd,
-        reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, P, C, mix_scale, relu);
+        reinterpret_cast<__nv_bfloat16*>(dx), ws, P, C, mix_scale, relu);
     TRIS_LAUNCH_OK("instnorm_bwd_kernel");
     return TRIS_OK;
 }

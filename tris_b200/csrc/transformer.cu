@@ -48,15 +48,46 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __res
     }
 }
 
-// dE[ids] += dx ; dP[l] += sum_n dx   (fp32 atomics into the flat gradient buffer)
-__global__ void embed_bwd_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ dx, float* __restrict__ dE,
-                                 float* __restrict__ dP, int L, int D) {
-    const int n = blockIdx.x;
-    for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
-        const int l = i / D, d = i % D;
-        const float g = __bfloat162float(dx[(static_cast<long>(n) * L + l) * D + d]);
-        atomicAdd(dE + static_cast<long>(ids[n * L + l]) * D + d, g);
-        atomicAdd(dP + l * D + d, g);
+// dE[ids] += dx ; dP[l] += sum_n dx, without atomics (bit-reproducible):
+//  * positional part: one thread per (l, d) adds the N samples in order;
+//  * token part: one CTA per token position i = n*L + l.  The CTA whose position is the FIRST occurrence of its token id owns
+//    that embedding row: it adds the rows of every later occurrence in position order (SOT / EOT occur in every sentence).
+__global__ void embed_bwd_pos_kernel(const __nv_bfloat16* __restrict__ dx, float* __restrict__ dP, int N, int L, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * D) return;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += __bfloat162float(dx[static_cast<long>(n) * L * D + i]);
+    dP[i] += s;
+}
+__global__ void __launch_bounds__(128) embed_bwd_tok_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ dx,
+                                                            float* __restrict__ dE, int T, int D) {
+    extern __shared__ int s_ids[];          // [T] token ids, then [T] positions sharing this CTA's id (owner CTAs only)
+    __shared__ int s_cnt;
+    const int me = blockIdx.x;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s_ids[i] = ids[i];
+    __syncthreads();
+    const int tok = s_ids[me];
+    int earlier = 0;
+    for (int j = threadIdx.x; j < me; j += blockDim.x) earlier |= (s_ids[j] == tok);
+    if (__syncthreads_or(earlier)) return;  // an earlier position owns this token's row
+    if (threadIdx.x == 0) {                 // ordered list of the later occurrences (shared-memory scan, owners only)
+        int cnt = 0;
+        for (int j = me; j < T; ++j)
+            if (s_ids[j] == tok) s_ids[T + cnt++] = j;
+        s_cnt = cnt;
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int k0 = 0; k0 < cnt; k0 += 8) {       // eight rows in flight, added in position order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = k0 + u < cnt ? __bfloat162float(dx[static_cast<long>(s_ids[T + k0 + u]) * D + d]) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        dE[static_cast<long>(tok) * D + d] += s;
     }
 }
 
@@ -127,11 +158,11 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ add,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows, int D) {
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ ws,
+                                                            int rows, int D) {
     extern __shared__ float sm[];   // [2*D] block partials of dgamma/dbeta
     const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool want_param = dgamma != nullptr;
+    const bool want_param = ws != nullptr;
     if (want_param) {
         for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
         __syncthreads();
@@ -179,17 +210,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         }
     }
     if (want_param) {
+        // fixed order: the warps add their partials to the block sums one after the other; the block sums become row
+        // blockIdx.x of the two planes ws[2][gridDim.x][D] (dgamma | dbeta), reduced in row order by the caller's queue
+        for (int w = 0; w < warps; ++w) {
+            if (wid == w) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
+                for (int i = 0; i < NV; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(&sm[(i * 32 + lane) * 8 + j], pg[i].v[j]);
-                atomicAdd(&sm[D + (i * 32 + lane) * 8 + j], pb[i].v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        sm[(i * 32 + lane) * 8 + j] += pg[i].v[j];
+                        sm[D + (i * 32 + lane) * 8 + j] += pb[i].v[j];
+                    }
             }
-        __syncthreads();
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < D; i += blockDim.x) {
-            atomicAdd(dgamma + i, sm[i]);
-            atomicAdd(dbeta + i, sm[D + i]);
+            ws[static_cast<long>(blockIdx.x) * D + i] = sm[i];
+            ws[(static_cast<long>(gridDim.x) + blockIdx.x) * D + i] = sm[D + i];
         }
     }
 }
@@ -429,7 +466,8 @@ __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const
     }
 }
 
-// out[c] += sum_r x[r, c]   (x bf16 [rows, N]); grid = (ceil(N/64), row_chunks), block = (64, 4)
+// ws[chunk][c] = sum over the chunk's rows of x[r, c]   (x bf16 [rows, N]); grid = (ceil(N/64), row_chunks), block = (64, 4).
+// Plain stores: the caller's queue adds the chunk rows in order into the bias gradient (bit-reproducible).
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int rows, int N) {
     __shared__ float part[4][64];
     const int c = blockIdx.x * 64 + threadIdx.x;
@@ -438,7 +476,8 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
         for (int r = blockIdx.y * 4 + threadIdx.y; r < rows; r += gridDim.y * 4) s += __bfloat162float(x[static_cast<long>(r) * N + c]);
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.y == 0 && c < N) atomicAdd(out + c, part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]);
+    if (threadIdx.y == 0 && c < N)
+        out[static_cast<long>(blockIdx.y) * N + c] = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
 }
 
 // ViT token assembly: tok[n,0,:] = cls + pos[0]; tok[n,1+p,:] = patch[n*P+p,:] + pos[1+p]
@@ -478,8 +517,14 @@ int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int*
 }
 
 int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, int L, int D, tris_stream_t stream) {
-    embed_bwd_kernel<<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, reinterpret_cast<const __nv_bfloat16*>(dx), dE, dP, L, D);
-    TRIS_LAUNCH_OK("embed_bwd_kernel");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* dxp = reinterpret_cast<const __nv_bfloat16*>(dx);
+    const int T = n * L;
+    if (2 * T * sizeof(int) > 48 * 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_embed_bwd: %d tokens exceed the shared-memory id table", T);
+    embed_bwd_pos_kernel<<<(L * D + 255) / 256, 256, 0, st>>>(dxp, dP, n, L, D);
+    TRIS_LAUNCH_OK("embed_bwd_pos_kernel");
+    embed_bwd_tok_kernel<<<T, 128, 2 * T * sizeof(int), st>>>(ids, dxp, dE, T, D);
+    TRIS_LAUNCH_OK("embed_bwd_tok_kernel");
     return TRIS_OK;
 }
 
@@ -502,22 +547,27 @@ int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
 }
 
 int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* add,
-                       void* dx, float* dgamma, float* dbeta, int rows, int D, tris_stream_t stream) {
+                       void* dx, float* ws, int ws_rows, int rows, int D, tris_stream_t stream) {
     if (D % 256 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: D=%d must be a multiple of 256, <= 1024", D);
     const int warps = 8;
     int grid = (rows + warps - 1) / warps;
-    const int cap = dgamma != nullptr ? tris::sm_count() : 4 * tris::sm_count();   // fewer blocks = fewer global atomics
-    if (grid > cap) grid = cap;
+    if (ws != nullptr) {
+        // parameter gradients: exactly ws_rows CTAs, each writes row blockIdx.x of ws[2][ws_rows][D]
+        if (ws_rows < 1 || ws_rows > grid) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: ws_rows %d not in 1..%d", ws_rows, grid);
+        grid = ws_rows;
+    } else if (grid > 4 * tris::sm_count()) {
+        grid = 4 * tris::sm_count();
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16*>(dy), *xp = reinterpret_cast<const __nv_bfloat16*>(x),
                         *ap = reinterpret_cast<const __nv_bfloat16*>(add);
     __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
     const size_t smb = 2 * D * sizeof(float);
     switch (D / 256) {
-        case 1: layernorm_bwd_kernel<1><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
-        case 2: layernorm_bwd_kernel<2><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
-        case 3: layernorm_bwd_kernel<3><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
-        default: layernorm_bwd_kernel<4><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, dgamma, dbeta, rows, D); break;
+        case 1: layernorm_bwd_kernel<1><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        case 2: layernorm_bwd_kernel<2><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        case 3: layernorm_bwd_kernel<3><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        default: layernorm_bwd_kernel<4><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
     }
     TRIS_LAUNCH_OK("layernorm_bwd_kernel");
     return TRIS_OK;
@@ -568,12 +618,10 @@ int tris_scatter_rows(const void* src, const int* idx, void* out, int rows, int 
     return TRIS_OK;
 }
 
-int tris_colsum(const void* x, float* out, int rows, int N, tris_stream_t stream) {
-    int chunks = (rows + 31) / 32;   // <= 8 rows per thread: the row loop is a chain of dependent-latency loads
-    if (chunks > 128) chunks = 128;
-    if (chunks < 1) chunks = 1;
+int tris_colsum(const void* x, float* ws, int chunks, int rows, int N, tris_stream_t stream) {
+    if (chunks < 1 || chunks > 65535) return tris::fail(TRIS_ERR_SHAPE, "tris_colsum: chunks %d", chunks);
     dim3 grid((N + 63) / 64, chunks);
-    colsum_kernel<<<grid, dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, N);
+    colsum_kernel<<<grid, dim3(64, 4), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ws, rows, N);
     TRIS_LAUNCH_OK("colsum_kernel");
     return TRIS_OK;
 }

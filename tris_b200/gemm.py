@@ -40,11 +40,67 @@ def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
 WGRAD_MAX_CTAS = int(os.environ.get("TRIS_WGRAD_CTAS", "0"))   # experiment: cap the SMs a side-stream weight gradient takes
 
 
+STAT_PARTS = 148   # rows of a partial-statistics buffer (ops.STAT_PARTS): one per CTA of the persistent kernel
+
+
 def _desc(**kw) -> L.GemmDesc:
     d = L.GemmDesc()
     for k, v in kw.items():
         setattr(d, k, v)
+    if d.stats:
+        d.stats_parts = STAT_PARTS
     return d
+
+
+def _bwd_stats(kw, bwd_stats):
+    """bwd_stats = (parts fp32 [STAT_PARTS*2N (+spare)], y bf16 (shape of the output), mean fp32 [N], mask_sc | None, mask_sh | None):
+    the epilogue stores g = out * [y*mask_sc + mask_sh > 0] and accumulates the BatchNorm-backward sums (sum g, sum g (y - mean))
+    of the stored g as partial rows -- the dgamma / dbeta reduction of the layer that produced y, fused into this GEMM."""
+    if bwd_stats is None:
+        return kw
+    parts, y, mean, msc, msh = bwd_stats
+    assert y.dtype == torch.bfloat16 and y.is_contiguous()
+    kw.update(stats=L.ptr(parts), stats_mode=1, stats_y=L.ptr(y), stats_mu=L.ptr(mean), mask_sc=L.ptr(msc), mask_sh=L.ptr(msh))
+    return kw
+
+
+class SplitKQueue:
+    """Pending second stages of split-K weight gradients (partials already stored to their workspaces by the GEMMs).
+    ``flush()`` reduces all of them -- in split order, bit-reproducible -- with ONE launch per 64 tensors, on the current
+    stream: call it on the stream the GEMMs ran on, before anything reads the gradients."""
+
+    def __init__(self):
+        self.items = []          # (ws tensor, out tensor, rows, w, ldd, split, accumulate)
+
+    def push(self, ws, out, rows, w, ldd, split, accumulate):
+        self.items.append((ws, out, rows, w, ldd, split, accumulate))
+
+    def flush(self):
+        if not self.items:
+            return
+        n = len(self.items)
+        arr = (L.ReduceItem * n)()
+        for i, (ws, out, rows, w, ldd, split, acc) in enumerate(self.items):
+            arr[i] = L.ReduceItem(ws.data_ptr(), out.data_ptr(), rows, w, ldd, split, int(acc), 0)
+        L.call("tris_splitk_reduce_multi", arr, n, launches=(n + 63) // 64)
+        self.items = []          # the caching allocator keeps the workspaces valid for the kernels already queued on this stream
+
+
+def _launch_wgrad(d, ws, out, rows, w, ldd, accumulate, queue):
+    """Run a (possibly split-K) weight-gradient GEMM; with a queue, its second stage is deferred to queue.flush()."""
+    split = d.split_k
+    if queue is not None and split > 1:
+        d.defer_reduce = 1
+        L.gemm_raw(d)
+        if d.split_used > 1:
+            queue.push(ws, out, rows, w, ldd, d.split_used, accumulate)
+    else:
+        L.gemm_raw(d, launches=2 if split > 1 else 1)
+
+
+def _ws(split, m, w, dev):
+    """fp32 workspace of a split-K weight gradient: [split][m][w]."""
+    return torch.empty((split * m * w,), device=dev, dtype=torch.float32) if split > 1 else None
 
 
 def _chk(t, dtype, name):
@@ -72,7 +128,7 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
 
 
 def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None, dact_src=None,
-                 act=L.ACT_NONE, bias=None):
+                 act=L.ACT_NONE, bias=None, bwd_stats=None):
     """dx[M,K] = dy[M,N] @ w[N,K]   (w read MN-major: no transposed weight copy)."""
     _chk(dy, torch.bfloat16, "dy"); _chk(w, torch.bfloat16, "w")
     m, n = dy.shape
@@ -84,9 +140,9 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
     bn = block_n or _bn_for(k, tiles_m, True)
     if out.dtype == torch.float32:
         bn = min(bn, 128)
-    d = _desc(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
+    d = _desc(**_bwd_stats(dict(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
               b_mode=L.OP_MN2D, M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1, act=act,
-              dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16)
+              dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16), bwd_stats))
     L.gemm_raw(d)
     return out
 
@@ -107,7 +163,7 @@ def _split_for(tiles: int, kblocks: int) -> int:
     return best
 
 
-def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
+def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None, queue=None):
     """dw[N,K] (f32) (+)= dy[M,N]^T @ x[M,K]  (both operands MN-major, contraction over rows, split-K)."""
     _chk(dy, torch.bfloat16, "dy"); _chk(x, torch.bfloat16, "x")
     m, n = dy.shape
@@ -118,15 +174,15 @@ def linear_wgrad(dy, x, out=None, accumulate=False, block_n=None, split_k=None):
     tiles = tiles_m * ((k + bn - 1) // bn)
     kblocks = (m + 63) // 64
     sk = split_k or _split_for(tiles, kblocks)
-    atomic = 1 if (sk > 1 or accumulate) else 0
+    sk = max(1, min(sk, kblocks))
     if out is None:
-        out = (torch.zeros if atomic else torch.empty)((n, k), device=dy.device, dtype=torch.float32)
-    elif atomic and not accumulate:
-        out.zero_()
+        out = (torch.zeros if accumulate else torch.empty)((n, k), device=dy.device, dtype=torch.float32)
     _chk(out, torch.float32, "out")
+    ws = _ws(sk, n, (k + 3) // 4 * 4, dy.device)
     d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, M=n, N=k, K=m, lda=n, ldb=k,
-              ldd=k, taps=1, block_n=bn, split_k=sk, out_dtype=L.DT_F32, atomic=atomic, max_ctas=WGRAD_MAX_CTAS)
-    L.gemm_raw(d)
+              ldd=k, taps=1, block_n=bn, split_k=sk, out_dtype=L.DT_F32, atomic=1 if accumulate else 0, max_ctas=WGRAD_MAX_CTAS,
+              splitk_ws=L.ptr(ws))
+    _launch_wgrad(d, ws, out, n, (k + 3) // 4 * 4, k, accumulate, queue)
     return out
 
 
@@ -175,7 +231,7 @@ def conv3x3_fwd(x, wp, stats=None, out=None, block_n=None, taps=9):
     return out
 
 
-def conv3x3_dgrad(dy, wp, cin, out=None, block_n=None):
+def conv3x3_dgrad(dy, wp, cin, out=None, block_n=None, bwd_stats=None):
     """dx[n,h,w,ci] = conv_transpose3x3(dy[n,h,w,co]); wp is the forward packing [co, 9*ci] read MN-major."""
     _chk(dy, torch.bfloat16, "dy"); _chk(wp, torch.bfloat16, "wp")
     n, h, w, co = dy.shape
@@ -185,14 +241,14 @@ def conv3x3_dgrad(dy, wp, cin, out=None, block_n=None):
     th, tw = conv_tile(h, w)
     tiles_m = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
     bn = block_n or _bn_for(cin, tiles_m, True)
-    d = _desc(a=L.ptr(dy), b=L.ptr(wp), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_MN2D, M=n * h * w, N=cin,
+    d = _desc(**_bwd_stats(dict(a=L.ptr(dy), b=L.ptr(wp), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_MN2D, M=n * h * w, N=cin,
               K=9 * co, ldb=9 * cin, ldd=cin, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, flip=1,
-              b_tap_stride=cin, block_n=bn, split_k=1, out_dtype=L.DT_BF16)
+              b_tap_stride=cin, block_n=bn, split_k=1, out_dtype=L.DT_BF16), bwd_stats))
     L.gemm_raw(d)
     return out
 
 
-def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
+def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None, queue=None):
     """dwp[co, 9*ci] (f32) = sum_pixels dy[.,co] * x[. + tap, ci]."""
     _chk(dy, torch.bfloat16, "dy"); _chk(x, torch.bfloat16, "x")
     n, h, w, co = dy.shape
@@ -203,16 +259,16 @@ def conv3x3_wgrad(dy, x, out=None, block_n=None, split_k=None):
     tiles_m = (co + 127) // 128
     bn = min(block_n or _bn_for(ci, 9 * tiles_m, True), 128)
     tiles = 9 * tiles_m * ((ci + bn - 1) // bn)
-    sk = split_k or _split_for(tiles, kblocks)
-    atomic = 1      # the conv weight-gradient epilogue always leaves through TMA reduce-add
+    sk = max(1, min(split_k or _split_for(tiles, kblocks), kblocks))
     if out is None:
-        out = torch.zeros((co, 9 * ci), device=dy.device, dtype=torch.float32)
-    else:
-        out.zero_()
+        out = torch.empty((co, 9 * ci), device=dy.device, dtype=torch.float32)
+    if sk == 1:
+        out.zero_()    # a single partial per tile leaves through TMA reduce-add (one add per element: order-free)
+    ws = _ws(sk, co, 9 * ci, dy.device)
     d = _desc(a=L.ptr(dy), b=L.ptr(x), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_CONV, M=co, N=ci, K=n * h * w,
               ldd=9 * ci, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, wgrad=1, block_n=bn, split_k=sk,
-              out_dtype=L.DT_F32, atomic=atomic, max_ctas=WGRAD_MAX_CTAS)
-    L.gemm_raw(d)
+              out_dtype=L.DT_F32, atomic=0, max_ctas=WGRAD_MAX_CTAS, splitk_ws=L.ptr(ws))
+    _launch_wgrad(d, ws, out, co, 9 * ci, 9 * ci, False, queue)
     return out
 
 
@@ -231,9 +287,12 @@ def gemm_ex(a, b, out, M, N, K, a_mode=L.OP_K2D, b_mode=L.OP_K2D, lda=None, ldb=
     bn = block_n or _bn_for(N, tiles_m, b_mode != L.OP_K2D)
     if f32:
         bn = min(bn, 128)
+    kblocks = (K + 63) // 64
+    split_k = max(1, min(split_k, kblocks))
+    ws = _ws(split_k, M, (N + 3) // 4 * 4, a.device)
     d = _desc(a=L.ptr(a), b=L.ptr(b), d=L.ptr(out), bias=L.ptr(bias), a_mode=a_mode, b_mode=b_mode, M=M, N=N, K=K, lda=lda,
               ldb=ldb, ldd=ldd, taps=1, block_n=bn, split_k=split_k, act=act, out_dtype=L.DT_F32 if f32 else L.DT_BF16,
               atomic=atomic, batch=batch, a_batch_stride=a_bs, b_batch_stride=b_bs, d_batch_stride=d_bs, scale=scale,
-              residual=L.ptr(residual))
-    L.gemm_raw(d)
+              residual=L.ptr(residual), splitk_ws=L.ptr(ws))
+    L.gemm_raw(d, launches=2 if split_k > 1 else 1)
     return out

@@ -116,16 +116,20 @@ class Stage1Head:
 
     # ------------------------------------------------------------------ backward
     def _wgrad(self, dy, x, gw):
-        """gw[N,K] (fp32, accumulated) += dy[M,N]^T x[M,K]."""
-        G.linear_wgrad(dy, x, out=gw, accumulate=True)
+        """gw[N,K] (fp32, accumulated) += dy[M,N]^T x[M,K]; split-K second stages are deferred to one launch at the end
+        of the backward (self._q.flush())."""
+        G.linear_wgrad(dy, x, out=gw, accumulate=True, queue=self._q)
 
     def _bwd(self, t, dcls, dfg, drelu, dsig, des):
         W, Pf, Gr = self._views("shadow"), self._views("flat"), self._views("grad")
+        self._q = G.SplitKQueue()
         B, h, w, Pn, T, Tp = t["dims"]
         C = self.C
         dev = t["nv"].device
         dmaps = ops.upsample_bwd(drelu, dsig, t["sig"], h, w) if (drelu is not None or dsig is not None) else None
-        D = ops.head_bwd(t["R"], Pf["ls"], dcls, dfg, dmaps, t["mbar"], t["am"], Gr["ls"], T, self.focal_p, self.focal_lambda)
+        dls = torch.empty((B,), device=dev, dtype=f32)
+        D = ops.head_bwd(t["R"], Pf["ls"], dcls, dfg, dmaps, t["mbar"], t["am"], dls, T, self.focal_p, self.focal_lambda)
+        Gr["ls"].add_(dls.sum())        # B per-image partials added in a fixed order (the kernel used to atomicAdd them)
         if des is not None:
             Gr["ls"].add_(des * Pf["ls"].exp())
         vp, lp, lp_bs = t["vp"], t["lp"], t["lp_bs"]
@@ -140,15 +144,15 @@ class Stage1Head:
             qt, kt, vt = At3[:, :C], At3[:, C:2 * C], At3[:, 2 * C:]
             # ---- v' = nv + 0.1 IN(Ov) ; Ov = nvp Wo^T + bo
             dOv = ops.instnorm_bwd(dvp, t["Ov"], Pf["go"], Pf["beo"], t["muo"], t["iso"], Gr["go"], Gr["beo"], B, relu=False,
-                                   mix_scale=MIX)
+                                   mix_scale=MIX, queue=self._q)
             self._wgrad(dOv, nvp, Gr["Wo"])
-            ops.colsum(dOv, Gr["bo"])
+            ops.colsum(dOv, Gr["bo"], queue=self._q)
             dnvp = G.linear_dgrad(dOv, W["Wo"])
             # ---- l'_b = nl + 0.1 (nlp_b Wto^T + bto)
             dnl = ops.batch_sum(dlp, (T, C))
             dOl = ops.axpby(dlp, dlp, MIX, 0.0)
             self._wgrad(dOl, nlp, Gr["Wto"])
-            ops.colsum(dOl, Gr["bto"])
+            ops.colsum(dOl, Gr["bto"], queue=self._q)
             dnlp = G.linear_dgrad(dOl, W["Wto"])
             # ---- nvp = PA Vt
             dPA = torch.empty((B, Pn, Tp), device=dev, dtype=f32)
@@ -170,24 +174,25 @@ class Stage1Head:
             # ---- text projections (ReLU, shared by all images)
             dYt = ops.relu_mask(dAt3, At3)
             self._wgrad(dYt, nl, Gr["Wt"])
-            ops.colsum(dYt, Gr["bt"])
+            ops.colsum(dYt, Gr["bt"], queue=self._q)
             dnl = G.linear_dgrad(dYt, W["Wt"], residual=dnl)
             # ---- visual projections (InstanceNorm + ReLU)
-            dYv = ops.instnorm_bwd(dA3, t["Yv"], Pf["gqkv"], Pf["beqkv"], t["mu3"], t["is3"], Gr["gqkv"], Gr["beqkv"], B, relu=True)
+            dYv = ops.instnorm_bwd(dA3, t["Yv"], Pf["gqkv"], Pf["beqkv"], t["mu3"], t["is3"], Gr["gqkv"], Gr["beqkv"], B, relu=True, queue=self._q)
             self._wgrad(dYv, t["nvc"], Gr["Wqkv"])
-            ops.colsum(dYv, Gr["bqkv"])
+            ops.colsum(dYv, Gr["bqkv"], queue=self._q)
             dnv = G.linear_dgrad(dYv, W["Wqkv"], residual=dvp)
         else:
             dnv = dvp
             dnl = ops.batch_sum(dlp, (T, C))
         dvis = ops.l2norm_bwd(dnv, nv, t["inv_v"])
         self._wgrad(dvis, t["X0"], Gr["Wv"])
-        ops.colsum(dvis, Gr["bv"])
+        ops.colsum(dvis, Gr["bv"], queue=self._q)
         dc4 = G.linear_dgrad(dvis, W["Wv"]).view(B, h, w, -1)
         dlan = ops.l2norm_bwd(dnl, nl, t["inv_l"])
         self._wgrad(dlan, t["hidden"], Gr["Wl"])
-        ops.colsum(dlan, Gr["bl"])
+        ops.colsum(dlan, Gr["bl"], queue=self._q)
         dhidden = G.linear_dgrad(dlan, W["Wl"])
+        self._q.flush()
         return dc4, dhidden
 
     @staticmethod

@@ -26,38 +26,57 @@ def empty(shape, like, dtype=bf16):
 # ------------------------------------------------------------------ BatchNorm family (NHWC)
 class BNState:
     """Per-layer BatchNorm tensors handed to the kernels (all fp32 [C])."""
-    __slots__ = ("gamma", "beta", "rm", "rv", "mean", "invstd", "dgamma", "dbeta")
+    __slots__ = ("gamma", "beta", "rm", "rv", "mean", "invstd", "dgamma", "dbeta", "scale", "shift")
 
     def __init__(self, gamma, beta, rm, rv, dgamma=None, dbeta=None):
         self.gamma, self.beta, self.rm, self.rv = gamma, beta, rm, rv
         self.mean = torch.empty_like(gamma)
         self.invstd = torch.empty_like(gamma)
+        self.scale = torch.empty_like(gamma)      # gamma * invstd, beta - mean * gamma * invstd of the last train-mode forward
+        self.shift = torch.empty_like(gamma)
         self.dgamma, self.dbeta = dgamma, dbeta
 
 
+STAT_PARTS = 148      # rows of a partial-statistics buffer: one per CTA of the persistent GEMM (= SMs of a B200)
+
+
 def bn_apply(y, stats, bn: BNState, train, relu=True, pool=1, y1=None, stats1=None, bn1: BNState = None, residual=None,
-             momentum=0.1, eps=1e-5):
+             momentum=0.1, eps=1e-5, fold_half=0):
+    """stats / stats1: the GEMM epilogue's partial rows [STAT_PARTS, 2C] (train mode); they are summed in a fixed order by
+    the finalize kernel that precedes the apply kernel."""
     n, h, w, c = y.shape
     out = empty((n, h // pool, w // pool, c), y)
     L.call("tris_bn_apply_fwd", _vp(y), _vp(stats), _vp(bn.gamma), _vp(bn.beta), _vp(bn.rm), _vp(bn.rv), _vp(bn.mean),
            _vp(bn.invstd), _vp(y1), _vp(stats1), _vp(bn1.gamma if bn1 else None), _vp(bn1.beta if bn1 else None),
            _vp(bn1.rm if bn1 else None), _vp(bn1.rv if bn1 else None), _vp(bn1.mean if bn1 else None),
            _vp(bn1.invstd if bn1 else None), _vp(residual), _vp(out), n, h, w, c, pool, int(relu), int(train),
-           C.c_float(momentum), C.c_float(eps))
+           C.c_float(momentum), C.c_float(eps), STAT_PARTS if train else 0, int(fold_half), _vp(bn.scale), _vp(bn.shift),
+           launches=2 if train else 1)
     return out
 
 
-def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False, fold_half=0):
-    """Returns (dy, dy1|None, g|None); accumulates dgamma/dbeta into bn.dgamma/bn.dbeta (fp32, pre-zeroed)."""
+_BN_BWD_PARTS = 4 * 148     # CTAs of the reduction kernel (4 resident per SM)
+
+
+def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False, fold_half=0, ext=None):
+    """Returns (dy, dy1|None, g|None); adds dgamma/dbeta into bn.dgamma/bn.dbeta (fp32).  The per-channel reductions are
+    two-stage in a private workspace (never in the gradient buffers) and bit-reproducible.
+    ext: partial rows [STAT_PARTS, 2C] (+ 2C spare floats) written by the GEMM that produced `dout` (gemm.py bwd_stats=):
+    `dout` is then the already masked gradient and the reduction kernel is skipped."""
     n, h, w, c = y.shape
     dy = torch.empty_like(y)
     dy1 = torch.empty_like(y1) if y1 is not None else None
     g = torch.empty_like(y) if want_g else None
+    k = 3 if y1 is not None else 2
+    if ext is not None:
+        ws, ext_parts = ext, STAT_PARTS
+    else:
+        ws, ext_parts = torch.empty(((_BN_BWD_PARTS + 1) * k * c,), device=y.device, dtype=f32), 0
     L.call("tris_bn_bwd", _vp(dout), _vp(out), _vp(y), _vp(bn.gamma), _vp(bn.beta), _vp(bn.mean), _vp(bn.invstd),
            _vp(bn.dgamma), _vp(bn.dbeta), _vp(dy), _vp(y1), _vp(bn1.gamma if bn1 else None),
            _vp(bn1.beta if bn1 else None), _vp(bn1.mean if bn1 else None), _vp(bn1.invstd if bn1 else None),
            _vp(bn1.dgamma if bn1 else None), _vp(bn1.dbeta if bn1 else None), _vp(dy1), _vp(g), n, h, w, c, pool,
-           int(relu), int(fold_half), launches=2 + (1 if fold_half else 0))
+           int(relu), int(fold_half), _vp(ws), C.c_long(ws.numel()), ext_parts, launches=3 if ext is None else 2)
     return dy, dy1, g
 
 
@@ -99,11 +118,29 @@ def layernorm_fwd(x, gamma, beta, save=True, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None):
+def _queue(queue):
+    """(queue to push to, flush-now flag): without a caller-owned gemm.SplitKQueue the reduction runs immediately."""
+    if queue is not None:
+        return queue, False
+    from .gemm import SplitKQueue
+    return SplitKQueue(), True
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, queue=None):
+    """dgamma / dbeta (fp32 [D], accumulated): per-CTA partial rows + an in-order sum through the queue (no atomics)."""
     rows, d = x.shape
     dx = torch.empty_like(x)
-    L.call("tris_layernorm_bwd", _vp(dy), _vp(x), _vp(gamma), _vp(mean), _vp(rstd), _vp(add), _vp(dx), _vp(dgamma),
-           _vp(dbeta), rows, d)
+    ws, nrows = None, 0
+    if dgamma is not None:
+        nrows = max(1, min((rows + 7) // 8, 148))
+        ws = torch.empty((2, nrows, d), device=x.device, dtype=f32)
+    L.call("tris_layernorm_bwd", _vp(dy), _vp(x), _vp(gamma), _vp(mean), _vp(rstd), _vp(add), _vp(dx), _vp(ws), nrows, rows, d)
+    if ws is not None:
+        q, now = _queue(queue)
+        q.push(ws[0], dgamma, 1, d, d, nrows, True)
+        q.push(ws[1], dbeta, 1, d, d, nrows, True)
+        if now:
+            q.flush()
     return dx
 
 
@@ -131,8 +168,17 @@ def scatter_rows(src, idx, rows_total):
     return out
 
 
-def colsum(x, out):
-    L.call("tris_colsum", _vp(x), _vp(out), x.shape[0], x.shape[1])
+def colsum(x, out, queue=None):
+    """out[c] += sum_r x[r, c] (bias gradients): chunk partial rows + an in-order sum through the queue (no atomics)."""
+    rows, n = x.shape
+    assert n % 4 == 0
+    chunks = max(1, min(128, (rows + 31) // 32))
+    ws = torch.empty((chunks, n), device=x.device, dtype=f32)
+    L.call("tris_colsum", _vp(x), _vp(ws), chunks, rows, n)
+    q, now = _queue(queue)
+    q.push(ws, out, 1, n, n, chunks, True)
+    if now:
+        q.flush()
 
 
 def vit_assemble(patch, cls, pos, n):
@@ -166,10 +212,6 @@ def pack_conv_blockdiag(w, out, reps=2):
 def unpack_conv_grad_blockdiag(gp, gw, reps=2):
     co, ci, kh, kw = gw.shape
     L.call("tris_unpack_conv_grad_blockdiag", _vp(gp), _vp(gw), co, ci, kh * kw, reps)
-
-
-def fold_pairs(a, b=None, c=None, half=32):
-    L.call("tris_fold_pairs", _vp(a), _vp(b), _vp(c), half)
 
 
 def f32_to_bf16(src, dst):
@@ -227,11 +269,17 @@ def instnorm_fwd(x, gamma, beta, batch, relu, mix_scale=1.0, mix_add=None, eps=1
     return out, mean, invstd
 
 
-def instnorm_bwd(dout, x, gamma, beta, mean, invstd, dgamma, dbeta, batch, relu, mix_scale=1.0):
+def instnorm_bwd(dout, x, gamma, beta, mean, invstd, dgamma, dbeta, batch, relu, mix_scale=1.0, queue=None):
     rows, c = x.shape
     dx = torch.empty_like(x)
-    L.call("tris_instnorm_bwd", _vp(dout), _vp(x), _vp(gamma), _vp(beta), _vp(mean), _vp(invstd), _vp(dx), _vp(dgamma),
-           _vp(dbeta), batch, rows // batch, c, C.c_float(mix_scale), int(relu))
+    ws = torch.empty((2, batch, c), device=x.device, dtype=f32)
+    L.call("tris_instnorm_bwd", _vp(dout), _vp(x), _vp(gamma), _vp(beta), _vp(mean), _vp(invstd), _vp(dx), _vp(ws),
+           batch, rows // batch, c, C.c_float(mix_scale), int(relu))
+    q, now = _queue(queue)
+    q.push(ws[0], dgamma, 1, c, c, batch, True)
+    q.push(ws[1], dbeta, 1, c, c, batch, True)
+    if now:
+        q.flush()
     return dx
 
 
@@ -294,7 +342,9 @@ def head_fwd(R, logit_scale, T, focal_p, focal_l, train):
 
 
 def head_bwd(R, logit_scale, dcls, dfg, dmaps, mbar, am, dlogit_scale, T, focal_p, focal_l):
+    """dlogit_scale: fp32 [B] per-image partial gradients of logit_scale (written, not accumulated)."""
     B, Pn, Tp = R.shape
+    assert dlogit_scale is None or dlogit_scale.numel() == B
     D = torch.empty((B, Pn, Tp), device=R.device, dtype=bf16)
     L.call("tris_head_bwd", _vp(R), _vp(logit_scale), _vp(dcls), _vp(dfg), _vp(dmaps), _vp(mbar), _vp(am), _vp(D), _vp(dlogit_scale),
            B, Pn, T, Tp, C.c_float(focal_p), C.c_float(focal_l))

@@ -22,6 +22,11 @@ from .ops import BNState
 
 bf16, f32 = torch.bfloat16, torch.float32
 PAIR_STEM = os.environ.get("TRIS_STEM_PAIR", "1") != "0"   # image-pair-packed stem for even batches
+# BatchNorm-backward reductions (sum g, sum g (y - mean)) fused into the epilogue of the GEMM that produces the upstream
+# gradient (which then stores the ReLU-masked g directly): removes one HBM pass per BatchNorm layer in backward
+# (measured round 2: with y read straight from global memory in the epilogue the GEMMs slow down by more than the
+# reduction kernels cost -- tools/bench_bn_fusion.py -- so the fusion is OFF by default until y is staged through TMA)
+FUSE_BN_BWD = os.environ.get("TRIS_FUSE_BN_BWD", "0") != "0"
 
 
 class _Block:
@@ -78,7 +83,11 @@ class ResNetTower:
         self.w_stem3 = torch.zeros((64, 9 * 64), device=dev, dtype=bf16)
         self.w3x3 = {blk.p: torch.empty((blk.planes, 9 * blk.planes), device=dev, dtype=bf16) for blk in self.blocks}
         n_stats = 2 * (64 * 2 + 128 + sum(b.planes * 2 + b.planes * 4 * (2 if b.down else 1) for b in self.blocks))
-        self.stats_buf = torch.zeros(n_stats, device=dev, dtype=f32)
+        # BatchNorm batch statistics: every conv GEMM writes ops.STAT_PARTS partial rows of [2C] (one per CTA, fixed order)
+        self.stats_buf = torch.zeros(n_stats * ops.STAT_PARTS, device=dev, dtype=f32)
+        self._wgq = None             # gemm.SplitKQueue of a running backward() (None: split-K second stages run immediately)
+        self._wg_post = []
+        self._wg_stream = None
         self.bn_keys = [k for k, _ in module.named_buffers() if k.startswith(prefix) and k.endswith("num_batches_tracked")
                         and "attnpool" not in k]
         self.nbt = [bufs[k] for k in self.bn_keys]
@@ -122,14 +131,12 @@ class ResNetTower:
         B, _, H, W = img.shape
         tape = {} if train else None
         so = [0]
-        if train:
-            self.stats_buf.zero_()
-
         def stats(c):
             if not train:
                 return None
-            s = self.stats_buf[so[0]: so[0] + 2 * c]
-            so[0] += 2 * c
+            n = 2 * c * ops.STAT_PARTS
+            s = self.stats_buf[so[0]: so[0] + n]       # every row is (re)written by the GEMM: no clearing needed
+            so[0] += n
             return s
 
         pair = PAIR_STEM and B % 2 == 0
@@ -192,19 +199,13 @@ class ResNetTower:
         col = ops.stem_im2col_pair(img.contiguous())
         s = stats(64)
         y1 = G.linear_fwd(col, self.w_pair1, stats=s).view(B2, H // 2, W // 2, 64)
-        if train:
-            ops.fold_pairs(s[:64], s[64:], half=32)
-        a1 = ops.bn_apply(y1, s, self.pair_bn[p + "bn1"], train)
+        a1 = ops.bn_apply(y1, s, self.pair_bn[p + "bn1"], train, fold_half=32 if train else 0)
         s2 = stats(64)
         y2 = G.conv3x3_fwd(a1, self.w_pair2, stats=s2)
-        if train:
-            ops.fold_pairs(s2[:64], s2[64:], half=32)
-        a2 = ops.bn_apply(y2, s2, self.pair_bn[p + "bn2"], train)
+        a2 = ops.bn_apply(y2, s2, self.pair_bn[p + "bn2"], train, fold_half=32 if train else 0)
         s3 = stats(128)
         y3 = G.conv3x3_fwd(a2, self.w_pair3, stats=s3)
-        if train:
-            ops.fold_pairs(s3[:128], s3[128:], half=64)
-        xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2)                  # [B/2, H/4, W/4, 128]
+        xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2, fold_half=64 if train else 0)   # [B/2, H/4, W/4, 128]
         x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64).contiguous()   # un-pair: layout only
         if train:
             for nm in ("bn1", "bn2", "bn3"):
@@ -253,6 +254,8 @@ class ResNetTower:
     def _wg_begin(self):
         from .engine import OVERLAP
         self._wg_stream = None
+        self._wgq = G.SplitKQueue()      # deferred split-K second stages of this backward pass (one launch at the end)
+        self._wg_post = []               # work that reads the reduced gradients (conv gradient un-packing)
         if OVERLAP:
             if not hasattr(self, "_wg_side"):
                 self._wg_side = torch.cuda.Stream()
@@ -262,10 +265,27 @@ class ResNetTower:
             self._wg_keep = []
 
     def _wg_end(self):
+        def finish():
+            self._wgq.flush()
+            for fn in self._wg_post:
+                fn()
+            self._wg_post = []
         if self._wg_stream is not None:
+            with torch.cuda.stream(self._wg_stream):
+                finish()
             self._wg_main.wait_stream(self._wg_stream)
             self._wg_keep = []
             self._wg_stream = None
+        else:
+            finish()
+        self._wgq = None
+
+    def _post(self, fn):
+        """Run fn after the deferred split-K reductions of this backward pass (immediately when nothing is deferred)."""
+        if self._wgq is None:
+            fn()
+        else:
+            self._wg_post.append(fn)
 
     def _wg(self, fn, *tensors):
         """Run fn() (a weight-gradient launch sequence reading `tensors`) on the side stream after everything issued so
@@ -280,10 +300,24 @@ class ResNetTower:
             fn()
 
     def _backward(self, tape, dout):
-        st, p = self.store, self.prefix
-        for blk in reversed(self.blocks):
-            dout = self._block_bwd(blk, tape[blk.p], dout)
+        ext = None      # partial sums of this block's bn3 backward, when the GEMM that produced `dout` already fused them
+        for i in reversed(range(len(self.blocks))):
+            blk = self.blocks[i]
+            prev = self.blocks[i - 1] if i > 0 else None
+            # this block's input-gradient GEMM can carry the bn3-backward reduction of the block in front of it when both
+            # are plain residual blocks (the join is "+ identity": mask = sign of the shared activation)
+            fuse_prev = FUSE_BN_BWD and prev is not None and not blk.down and not prev.down
+            dout, ext = self._block_bwd(blk, tape[blk.p], dout, ext, prev if fuse_prev else None,
+                                        tape[prev.p] if fuse_prev else None)
         self._stem_bwd(tape["stem"], dout)
+
+    def _parts(self, c):
+        """Partial-sum rows [STAT_PARTS, 2c] of a fused BatchNorm-backward reduction (+ 2c floats for the finalized sums)."""
+        return torch.empty((ops.STAT_PARTS * 2 * c + 2 * c,), device=self.store.device, dtype=f32)
+
+    def _bwd_stats(self, y, bn, mask=True):
+        parts = self._parts(y.shape[-1])
+        return parts, (parts, y, bn.mean, bn.scale if mask else None, bn.shift if mask else None)
 
     def _stem_bwd(self, stem_rec, dout):
         st, p = self.store, self.prefix
@@ -303,9 +337,9 @@ class ResNetTower:
         dy1, _, _ = ops.bn_bwd(da1, None, y1, pb1)
 
         def stem1():
-            gw = G.linear_wgrad(dy1.view(-1, 64), col)                   # [64, 64] fp32
+            gw = G.linear_wgrad(dy1.view(-1, 64), col, queue=self._wgq)   # [64, 64] fp32
             g1 = st.g(p + "conv1.weight")                                # [32,3,3,3]
-            g1.add_(gw[:32, :27].reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+            self._post(lambda: g1.add_(gw[:32, :27].reshape(32, 3, 3, 3).permute(0, 3, 1, 2)))
         self._wg(stem1, dy1, col)
         for nm, pad in (("bn1", pb1), ("bn2", pb2)):
             st.g(p + nm + ".weight").add_(pad.dgamma[:32])
@@ -321,16 +355,18 @@ class ResNetTower:
         dxp = dout.reshape(B2, 2, h4, w4, 64).permute(0, 2, 3, 1, 4).reshape(B2, h4, w4, 128).contiguous()   # re-pair: layout only
         dy3, _, _ = ops.bn_bwd(dxp, None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64)
         self._wgrad3x3_pair(dy3, a2, p + "conv3.weight")
-        da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64)
-        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.pair_bn[p + "bn2"], fold_half=32)
+        ext2, bs2 = self._bwd_stats(y2, self.pair_bn[p + "bn2"]) if FUSE_BN_BWD else (None, None)
+        da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64, bwd_stats=bs2)
+        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.pair_bn[p + "bn2"], fold_half=32, ext=ext2)
         self._wgrad3x3_pair(dy2, a1, p + "conv2.weight")
-        da1 = G.conv3x3_dgrad(dy2, self.w_pair2, 64)
-        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.pair_bn[p + "bn1"], fold_half=32)
+        ext1, bs1 = self._bwd_stats(y1, self.pair_bn[p + "bn1"]) if FUSE_BN_BWD else (None, None)
+        da1 = G.conv3x3_dgrad(dy2, self.w_pair2, 64, bwd_stats=bs1)
+        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.pair_bn[p + "bn1"], fold_half=32, ext=ext1)
 
         def stem1():
-            gw = G.linear_wgrad(dy1.view(-1, 64), col)                   # [64, 64] fp32, two diagonal 32 x 27 blocks
+            gw = G.linear_wgrad(dy1.view(-1, 64), col, queue=self._wgq)   # [64, 64] fp32, two diagonal 32 x 27 blocks
             g1 = st.g(p + "conv1.weight")
-            g1.add_((gw[:32, :27] + gw[32:, 32:59]).reshape(32, 3, 3, 3).permute(0, 3, 1, 2))
+            self._post(lambda: g1.add_((gw[:32, :27] + gw[32:, 32:59]).reshape(32, 3, 3, 3).permute(0, 3, 1, 2)))
         self._wg(stem1, dy1, col)
         for nm in ("bn1", "bn2", "bn3"):     # folded sums hold the pair AVERAGE: the full-batch gradient is twice that
             pr = self.pair_bn[p + nm]
@@ -342,36 +378,43 @@ class ResNetTower:
         gw = self.store.g(key)
 
         def run():
-            gp = G.conv3x3_wgrad(dy, x)
-            ops.unpack_conv_grad_blockdiag(gp, gw, 2)
+            gp = G.conv3x3_wgrad(dy, x, queue=self._wgq)
+            self._post(lambda: ops.unpack_conv_grad_blockdiag(gp, gw, 2))
         self._wg(run, dy, x)
 
     def _wgrad3x3(self, dy, x, key, ci_pad=None):
         gw = self.store.g(key)
 
         def run():
-            gp = G.conv3x3_wgrad(dy, x)
-            ops.unpack_conv_grad(gp, gw, ci_pad=ci_pad)
+            gp = G.conv3x3_wgrad(dy, x, queue=self._wgq)
+            self._post(lambda: ops.unpack_conv_grad(gp, gw, ci_pad=ci_pad))
         self._wg(run, dy, x)
 
     def _wgrad1x1(self, dy2d, x2d, key):
         gw = self.store.g(key)
-        self._wg(lambda: G.linear_wgrad(dy2d, x2d, out=gw.view(gw.shape[0], gw.shape[1]), accumulate=True), dy2d, x2d)
+        self._wg(lambda: G.linear_wgrad(dy2d, x2d, out=gw.view(gw.shape[0], gw.shape[1]), accumulate=True, queue=self._wgq),
+                 dy2d, x2d)
 
-    def _block_bwd(self, blk: _Block, rec, dout):
+    def _block_bwd(self, blk: _Block, rec, dout, ext=None, prev=None, prev_rec=None):
+        """-> (dx, ext_prev).  ext: fused partial sums of this block's bn3 (then `dout` is the masked gradient g).
+        prev / prev_rec: the block in front, when this block's input-gradient GEMM is to fuse ITS bn3 reduction."""
         x, y1, a1, y2, a2, y3, xp, yd, out = rec
         q, pl = blk.p, blk.planes
         Cin = x.shape[3]
         if blk.down:
             dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], y1=yd, bn1=self.bn[q + "downsample.1"])
+        elif ext is not None:
+            dy3, dyd, g = ops.bn_bwd(dout, None, y3, self.bn[q + "bn3"], ext=ext)[0], None, dout
         else:
             dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], want_g=True)
         self._wgrad1x1(dy3.view(-1, 4 * pl), a2.view(-1, pl), q + "conv3.weight")
-        da2 = G.linear_dgrad(dy3.view(-1, 4 * pl), self._w1x1(q + "conv3.weight")).view(a2.shape)
-        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.bn[q + "bn2"], pool=blk.stride)
+        ext2, bs2 = self._bwd_stats(y2, self.bn[q + "bn2"]) if (FUSE_BN_BWD and blk.stride == 1) else (None, None)
+        da2 = G.linear_dgrad(dy3.view(-1, 4 * pl), self._w1x1(q + "conv3.weight"), bwd_stats=bs2).view(a2.shape)
+        dy2, _, _ = ops.bn_bwd(da2, None, y2, self.bn[q + "bn2"], pool=blk.stride, ext=ext2)
         self._wgrad3x3(dy2, a1, q + "conv2.weight")
-        da1 = G.conv3x3_dgrad(dy2, self.w3x3[q], pl)
-        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.bn[q + "bn1"])
+        ext1, bs1 = self._bwd_stats(y1, self.bn[q + "bn1"]) if FUSE_BN_BWD else (None, None)
+        da1 = G.conv3x3_dgrad(dy2, self.w3x3[q], pl, bwd_stats=bs1)
+        dy1, _, _ = ops.bn_bwd(da1, None, y1, self.bn[q + "bn1"], ext=ext1)
         self._wgrad1x1(dy1.view(-1, pl), x.view(-1, Cin), q + "conv1.weight")
         w1 = self._w1x1(q + "conv1.weight")
         if blk.down:
@@ -382,6 +425,13 @@ class ResNetTower:
                 dx = ops.avgpool2_bwd(dxp.view(xp.shape), add=dx)
             else:
                 dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=dxp).view(x.shape)
-        else:
-            dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin)).view(x.shape)
-        return dx
+            return dx, None
+        if prev is not None:
+            # x is the previous block's output relu(bn3(y3') + identity'): this GEMM stores g' = (dy1 W1 + g) * [x > 0] and the
+            # partial sums (sum g', sum g' (y3' - mean')) of the previous block's bn3 backward
+            extp, bsp = self._bwd_stats(prev_rec[5], self.bn[prev.p + "bn3"], mask=False)
+            dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin), dact_src=x.view(-1, Cin), act=ops.L.ACT_RELU,
+                                bwd_stats=bsp).view(x.shape)
+            return dx, extp
+        dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin)).view(x.shape)
+        return dx, None

@@ -43,31 +43,32 @@ class TransformerStack:
             x = x2
         return x, tape
 
-    def backward(self, tape, dx, n, l, param_grads: bool):
+    def backward(self, tape, dx, n, l, param_grads: bool, queue=None):
+        """queue: gemm.SplitKQueue collecting the split-K second stages of the weight gradients (the caller flushes it)."""
         st = self.st
         for i in reversed(range(self.layers)):
             k = lambda nm: self._k(i, nm)
             x, m1, r1, h, qkv, a, x1, m2, r2, h2, pre, u = tape[i]
             g = (lambda nm: st.g(k(nm))) if param_grads else (lambda nm: None)
             if param_grads:
-                G.linear_wgrad(dx, u, out=g("mlp.c_proj.weight"), accumulate=True)
-                ops.colsum(dx, g("mlp.c_proj.bias"))
+                G.linear_wgrad(dx, u, out=g("mlp.c_proj.weight"), accumulate=True, queue=queue)
+                ops.colsum(dx, g("mlp.c_proj.bias"), queue=queue)
             dpre = G.linear_dgrad(dx, st.s(k("mlp.c_proj.weight")), dact_src=pre, act=L.ACT_QUICKGELU)
             if param_grads:
-                G.linear_wgrad(dpre, h2, out=g("mlp.c_fc.weight"), accumulate=True)
-                ops.colsum(dpre, g("mlp.c_fc.bias"))
+                G.linear_wgrad(dpre, h2, out=g("mlp.c_fc.weight"), accumulate=True, queue=queue)
+                ops.colsum(dpre, g("mlp.c_fc.bias"), queue=queue)
             dh2 = G.linear_dgrad(dpre, st.s(k("mlp.c_fc.weight")))
-            dx1 = ops.layernorm_bwd(dh2, x1, st.p(k("ln_2.weight")), m2, r2, add=dx, dgamma=g("ln_2.weight"), dbeta=g("ln_2.bias"))
+            dx1 = ops.layernorm_bwd(dh2, x1, st.p(k("ln_2.weight")), m2, r2, add=dx, dgamma=g("ln_2.weight"), dbeta=g("ln_2.bias"), queue=queue)
             if param_grads:
-                G.linear_wgrad(dx1, a, out=g("attn.out_proj.weight"), accumulate=True)
-                ops.colsum(dx1, g("attn.out_proj.bias"))
+                G.linear_wgrad(dx1, a, out=g("attn.out_proj.weight"), accumulate=True, queue=queue)
+                ops.colsum(dx1, g("attn.out_proj.bias"), queue=queue)
             da = G.linear_dgrad(dx1, st.s(k("attn.out_proj.weight")))
             dqkv = ops.attn_bwd(qkv, da, n, l, self.heads, self.causal)
             if param_grads:
-                G.linear_wgrad(dqkv, h, out=g("attn.in_proj_weight"), accumulate=True)
-                ops.colsum(dqkv, g("attn.in_proj_bias"))
+                G.linear_wgrad(dqkv, h, out=g("attn.in_proj_weight"), accumulate=True, queue=queue)
+                ops.colsum(dqkv, g("attn.in_proj_bias"), queue=queue)
             dh = G.linear_dgrad(dqkv, st.s(k("attn.in_proj_weight")))
-            dx = ops.layernorm_bwd(dh, x, st.p(k("ln_1.weight")), m1, r1, add=dx1, dgamma=g("ln_1.weight"), dbeta=g("ln_1.bias"))
+            dx = ops.layernorm_bwd(dh, x, st.p(k("ln_1.weight")), m1, r1, add=dx1, dgamma=g("ln_1.weight"), dbeta=g("ln_1.bias"), queue=queue)
         return dx
 
 
@@ -96,12 +97,14 @@ class TextTower:
         st, p = self.st, self.prefix
         ids, eot, tape, xe, xn, m, r, rows = rec
         n, l = ids.shape
-        G.linear_wgrad(xn, dhidden, out=st.g(p + "text_projection"), accumulate=True)
+        q = G.SplitKQueue()
+        G.linear_wgrad(xn, dhidden, out=st.g(p + "text_projection"), accumulate=True, queue=q)
         dxn = G.linear_fwd(dhidden, st.s(p + "text_projection"))         # [N,E] @ [W,E]^T
         dxe = ops.layernorm_bwd(dxn, xe, st.p(p + "ln_final.weight"), m, r, dgamma=st.g(p + "ln_final.weight"),
-                                dbeta=st.g(p + "ln_final.bias"))
+                                dbeta=st.g(p + "ln_final.bias"), queue=q)
         dx = ops.scatter_rows(dxe, eot, rows)
-        dx0 = self.stack.backward(tape, dx, n, l, True)
+        dx0 = self.stack.backward(tape, dx, n, l, True, queue=q)
+        q.flush()          # one launch: all split-K weight-gradient partials of the tower, added in split order
         ops.embed_bwd(ids, dx0, st.g(p + "token_embedding.weight"), st.g(p + "positional_embedding"))
 
 

@@ -120,7 +120,7 @@ def main(args):
     t0 = time.time()
     if args.prms:
         aux, _ = clip.load("ViT-B/32", device="cuda", jit=False, txt_length=args.max_query_len,
-                           allow_random_init=args.synthetic_weights)
+                           allow_random_init=getattr(args, "synthetic_weights", None))
         miou = validate_same_sentence(args, refs, model, aux, rank)
         torch.cuda.synchronize()
         print(f"rank {rank}: PRMS mIoU {miou:.4f}  {len(dp.shard_range(args.val_refs, rank, world)) / (time.time() - t0):.1f} refs/s")
