@@ -1,8 +1,9 @@
 """GPU parity of the product (tris_b200.TRIS + Stage1 step) against the golden vectors produced by the UNMODIFIED
 reference (tests/golden/stage1_golden.npz) and against the CPU oracle on the same seeded inputs.
 
-Tolerances (north_star): bf16 path -> loss within 1e-2 rel; response maps are compared at 3e-2 of their range in
-bf16 mode (the 1e-3 fp32/tf32 mode is a later-round item)."""
+Tolerances (north_star): bf16 path -> loss within 1e-2 rel (batch 3, 8 at 2e-2, and 48 over five seeds); train-mode outputs at
+5e-2 (cls) / 1e-1 (maps) of their range; the 1e-3 fp32 response-map criterion is tests/test_precise_gpu.py.  The step is
+bit-reproducible (test_step_is_bit_reproducible)."""
 import argparse
 
 import numpy as np
@@ -65,13 +66,14 @@ def test_train_forward_vs_reference_golden(setup, golden):
     # that follows the attention output (model/attn.py:102-105 normalises a nearly pixel-constant tensor to unit
     # variance); the same figures come out of the fp32 oracle when its activations are rounded to bf16
     # (tools/debug_compare.py, DESIGN.md "precision").  The north-star bf16 criterion is the LOSS (next test).
-    # Two runs of this very code differ by 3 % at c4 / 8 % in cls / 19 % in the maps (tools/debug_determinism.py):
-    # atomics-order changes in the BN sums flip single bf16 roundings in the stem and the random-init train-mode
-    # network amplifies them.  Kernel correctness is pinned by the per-op tests (test_ops_gpu.py, test_gemm_gpu.py).
-    assert rel(cls, golden["cls_out"]) < 0.2
-    assert rel(cls_fg, golden["cls_fg"]) < 5e-2
-    assert rel(sig[:, :, ::s, ::s], golden["sig_sub"]) < 0.4
-    assert rel(relu_map[:, :, ::s, ::s], golden["relu_sub"]) < 0.4
+    # (Round 1: two runs of the same code differed by 3 % at c4 / 8 % in cls / 19 % in the maps because atomics-order changes
+    # in the BN sums flipped single bf16 roundings that the random-init train-mode network amplifies.  The step is now
+    # bit-reproducible (test_step_is_bit_reproducible), so these gates hold ONE deterministic realisation of that noise:
+    # batch of 3, BatchNorm statistics of layer4 over 300 pixels.)  Kernel correctness is pinned by the per-op tests.
+    assert rel(cls, golden["cls_out"]) < 5e-2          # measured 1.7e-2
+    assert rel(cls_fg, golden["cls_fg"]) < 3e-2        # measured 0.9e-2
+    assert rel(sig[:, :, ::s, ::s], golden["sig_sub"]) < 1e-1     # measured 6.1e-2
+    assert rel(relu_map[:, :, ::s, ::s], golden["relu_sub"]) < 1e-1   # measured 6.2e-2
     assert abs(ls.item() - float(golden["logit_scale_exp"])) < 1e-3
 
 
@@ -85,11 +87,10 @@ def test_step_losses_and_grads_vs_reference_golden(setup, golden):
     got = np.array([losses[k].item() for k in ("loss", "l1", "l4", "l5")])
     ref = golden["losses"]
     print("losses", got, ref)
-    # north-star bf16 criterion: loss within 1e-2 rel.  At this batch of 3 the bf16 rounding noise of the ~100 stored
-    # activation tensors decorrelates from run to run (atomics order) and moves the loss by 0.1 % - 2 %, so the gate
-    # here is 3e-2; test_loss_batch_mean_within_1e2 averages the noise out over repeated runs.
-    assert abs(got[0] - ref[0]) / abs(ref[0]) < 3e-2
-    assert np.all(np.abs(got - ref) < 4e-2 * np.abs(ref) + 2e-2)
+    # north-star bf16 criterion: loss within 1e-2 rel -- held here too (batch of 3, measured 0.44 %; the step is
+    # bit-reproducible since round 2, so this is one fixed realisation of the bf16 rounding noise, not a lucky draw)
+    assert abs(got[0] - ref[0]) / abs(ref[0]) < 1e-2
+    assert np.all(np.abs(got - ref) < 1e-2 * np.abs(ref) + 1e-3)
     # gradient norms: cosine-level agreement in bf16 (per-tensor norm within 10%, global within 3%)
     names = [str(n) for n in golden["grad_names"]]
     norms = golden["grad_norms"]
@@ -140,17 +141,18 @@ def test_loss_batch_mean_small_batch(setup, golden):
     m.load_state_dict(sd0)
     ref = float(golden["losses"][0])
     print("loss samples", vals, "ref", ref, "terms", [x.item() for x in (last["l1"], last["l4"], last["l5"])], golden["losses"])
-    assert abs(np.mean(vals) - ref) / ref < 3e-2
+    assert abs(np.mean(vals) - ref) / ref < 1e-2 and max(vals) == min(vals)     # deterministic: all evaluations identical
 
 
-@pytest.mark.parametrize("B,tol", [(8, 2e-2), (48, 1.5e-2)])
-def test_loss_vs_oracle_at_bench_batch(setup, B, tol):
+@pytest.mark.parametrize("B,seed,tol", [(8, 4321, 2e-2), (48, 1234, 1e-2), (48, 4321, 1e-2), (48, 7, 1e-2), (48, 99, 1e-2), (48, 2024, 1e-2)])
+def test_loss_vs_oracle_at_bench_batch(setup, B, seed, tol):
     """North-star bf16 criterion: loss within 1e-2 rel of the fp32 reference arithmetic at the benchmark configuration
-    (batch 48, 320x320, len 20, 3 negatives); batch 8 is held to 2e-2 (the small-batch bias of the classification term
-    described in test_loss_batch_mean_small_batch shrinks with the batch: ~2 % at 3, ~1 % at 8; at 48 the measured loss
-    error is 0.03-0.4 % for most batches with 1.1 % the worst seen (seed 4321), hence the 1.5e-2 gate; tools/debug_tower_noise.py
-    shows where the bf16 storage noise of the image tower enters).  The oracle (oracle/tris_oracle.py, pinned against the
-    unmodified reference by tests/test_oracle.py) is evaluated in fp32 on the GPU here so that a batch of 48 takes seconds."""
+    (batch 48, 320x320, len 20, 3 negatives) -- held for FIVE seeds.  Measured round 2 against the unmodified reference in
+    true fp32 on the same GPU (profiles/r2_autocast_bias_b48.txt): 0.80 / 0.54 / 0.65 / 0.18 / 0.19 %; the reference itself
+    under torch.autocast(bfloat16) deviates by 0.20 / 0.12 / 0.16 / 0.92 / 0.19 %.  Batch 8 is held to 2e-2 (the small-batch
+    bias of the classification term described in test_loss_batch_mean_small_batch shrinks with the batch).  The oracle
+    (oracle/tris_oracle.py, pinned against the unmodified reference by tests/test_oracle.py) is evaluated in fp32 on the GPU
+    here so that a batch of 48 takes seconds."""
     from oracle import tris_oracle as O
     from oracle import weights as W
     from tris_b200.train_step import stage1_losses
@@ -158,7 +160,7 @@ def test_loss_vs_oracle_at_bench_batch(setup, B, tol):
     torch.backends.cuda.matmul.allow_tf32 = False
     m, aux = setup["model"].train(), setup["aux"]
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
-    img, ids, negs = (t.cuda() for t in W.synthetic_batch(B, 320, 20, 3, 4321))
+    img, ids, negs = (t.cuda() for t in W.synthetic_batch(B, 320, 20, 3, seed))
     sdc = {k: v.clone() for k, v in sd0.items()}
     auxc = {k: v.detach().clone() for k, v in aux.state_dict().items()}
     with torch.no_grad():
@@ -166,6 +168,33 @@ def test_loss_vs_oracle_at_bench_batch(setup, B, tol):
         ref = O.stage1_losses(cls_out, sig_map, img, ids, negs, auxc)
         got = stage1_losses(m, aux, img, ids, negs)
     m.load_state_dict(sd0)
-    print({k: (got[k].item(), ref[k].item()) for k in ("loss", "l1", "l4", "l5")})
-    for k in ("loss", "l1", "l4", "l5"):
-        assert abs(got[k].item() - ref[k].item()) < tol * abs(ref[k].item()), (k, got[k].item(), ref[k].item())
+    print(B, seed, {k: (got[k].item(), ref[k].item()) for k in ("loss", "l1", "l4", "l5")})
+    assert abs(got["loss"].item() - ref["loss"].item()) < tol * abs(ref["loss"].item()), (got["loss"].item(), ref["loss"].item())
+    for k in ("l1", "l4", "l5"):
+        assert abs(got[k].item() - ref[k].item()) < max(tol, 1.2e-2) * abs(ref[k].item()), (k, got[k].item(), ref[k].item())
+
+
+def test_step_is_bit_reproducible(setup):
+    """Two forward+backward passes from the same state give IDENTICAL bits: the four losses and the whole flat gradient
+    buffer (98.8 M values).  Round 1 accumulated BatchNorm sums, split-K partials and bias / LayerNorm gradients with
+    floating-point atomics in arrival order; every reduction is now two-stage in a fixed order."""
+    from tris_b200.train_step import stage1_losses
+    m, aux = setup["model"].train(), setup["aux"]
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    st = m.engine().store
+    runs = []
+    for _ in range(3):
+        m.load_state_dict(sd0)
+        m.zero_grad(set_to_none=True)
+        st.zero_grad()
+        losses = stage1_losses(m, aux, setup["img"], setup["ids"], setup["negs"])
+        losses["loss"].backward()
+        torch.cuda.synchronize()
+        runs.append((torch.stack([losses[k].detach() for k in ("loss", "l1", "l4", "l5")]).clone(), st.grad.clone(),
+                     {k: v.clone() for k, v in m.state_dict().items() if "running" in k}))
+    m.load_state_dict(sd0)
+    for r in runs[1:]:
+        assert torch.equal(runs[0][0], r[0]), (runs[0][0], r[0])
+        assert torch.equal(runs[0][1], r[1]), f"{(runs[0][1] != r[1]).sum().item()} gradient values differ between identical runs"
+        for k, v in runs[0][2].items():
+            assert torch.equal(v, r[2][k]), k
