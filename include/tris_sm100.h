@@ -225,6 +225,11 @@ int tris_axpby(const void* x, void* y, float a, float b, long n, tris_stream_t s
 int tris_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long n, long n_group0, int* step,
     float max_iter, float lr0, float lr1, float beta1, float beta2, float eps, float wd, float grad_scale, float
     power, tris_stream_t stream);
+/* Device-side signal between a captured step graph and the communication stream (data-parallel overlap of the gradient
+ * all-reduce with the image-tower backward, train_stage1.py:68-70): tris_flag_inc bumps *flag from inside the graph,
+ * tris_flag_wait parks a one-thread kernel on `stream` until *flag has reached `target` (bounded spin, traps after ~10 s). */
+int tris_flag_inc(uint32_t* flag, tris_stream_t stream);
+int tris_flag_wait(const uint32_t* flag, uint32_t target, tris_stream_t stream);
 
 /* ---- transformer.cu */
 /* token_embedding[ids] + positional_embedding, EOT index = argmax(ids) (model.py:552-564). */

@@ -53,6 +53,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
 
 __global__ void tick_kernel(int* step) { *step += 1; }
 
+// Cross-graph signal for the overlapped gradient all-reduce: a kernel INSIDE the captured step bumps a device counter when
+// the gradients behind the image tower are final; a one-thread kernel on the communication stream (outside the graph) holds
+// the NCCL all-reduce queued behind it until the counter reaches the step number.  Bounded spin: a lost signal traps.
+__global__ void flag_inc_kernel(unsigned* flag) {
+    __threadfence();
+    atomicAdd(flag, 1u);
+}
+__global__ void flag_wait_kernel(const unsigned* flag, unsigned target) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (static_cast<int>(v - target) >= 0) break;
+        if (clock64() - t0 > 20000000000ll) __trap();      // ~10 s
+        __nanosleep(200);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -68,6 +86,18 @@ int tris_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, 
     TRIS_LAUNCH_OK("adamw_kernel");
     tick_kernel<<<1, 1, 0, s>>>(step);
     TRIS_LAUNCH_OK("tick_kernel");
+    return TRIS_OK;
+}
+
+int tris_flag_inc(uint32_t* flag, tris_stream_t stream) {
+    flag_inc_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flag);
+    TRIS_LAUNCH_OK("flag_inc_kernel");
+    return TRIS_OK;
+}
+
+int tris_flag_wait(const uint32_t* flag, uint32_t target, tris_stream_t stream) {
+    flag_wait_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flag, target);
+    TRIS_LAUNCH_OK("flag_wait_kernel");
     return TRIS_OK;
 }
 

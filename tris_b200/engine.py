@@ -241,6 +241,11 @@ class _TextFn(torch.autograd.Function):
         ctx.eng.begin_backward(ctx.fid)
         ctx.eng.text.backward(ctx.rec, dh.contiguous())
         ctx.rec = None
+        # head + text-tower gradients (everything behind the image tower in the flat buffer) are final on this stream: a
+        # data-parallel trainer starts their all-reduce here, under the RN50 backward (train_step.Stage1Trainer)
+        hook = getattr(ctx.eng, "on_text_grads_ready", None)
+        if hook is not None:
+            hook()
         return None, None, None
 
 

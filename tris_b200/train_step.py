@@ -77,13 +77,60 @@ class Stage1Trainer:
         dp.broadcast_parameters(st.flat, process_group)      # every rank starts from rank 0's weights (DDP semantics)
         self.graph = None
         self.static = None
+        # data parallel: the flat gradient buffer is [text head | image tower | text transformer + embeddings | new modules].
+        # Everything behind the image tower (76 % of the payload) is final when the text-tower backward ends, early in the
+        # RN50 backward: its all-reduce is issued there (engine._TextFn.backward hook) and overlaps the RN50 backward; the
+        # image-tower prefix follows after the backward.  Two NCCL calls per step, the first one hidden.
+        self._early_lo = None
+        self._early_work = None
+        self._graph_has_optimizer = True
+        self._graph_signals = False
+        self._flag = torch.zeros(1, device=st.device, dtype=torch.int32)
+        self._flag_target = 0
+        self._comm = torch.cuda.Stream(device=st.device) if self.world > 1 else None
+        # STATUS (round 2): correct and bit-exact in eager steps (tests/dp_equivalence_worker.py, 2 GPUs), but the CUDA-graph
+        # step hangs with it on this stack (both with NCCL captured in the graph and with the flag-released variant below),
+        # so it is opt-in: TRIS_DP_OVERLAP=1.  Default = one all-reduce of the whole buffer after the replay, as in round 1.
+        if self.world > 1 and os.environ.get("TRIS_DP_OVERLAP", "0") == "1":
+            vis = [k for k in st.trainable if k.startswith("backbone.visual.")]
+            if vis:
+                last = max(st.offsets[k] + (st.shapes[k].numel() + 7) // 8 * 8 for k in vis)
+                if 0 < last < st.n_train:
+                    self._early_lo = last
+                    self.eng.on_text_grads_ready = self._early_all_reduce
         st.publish_grads()            # param.grad = views of the flat buffer; the trainer zeroes the buffer itself
         for k in self.eng.extra_grad_keys:
             st.params[k].grad = st.g(k)
 
+    def _early_all_reduce(self):
+        """Called on the stream of the text-tower backward once every gradient behind the image tower is final.
+        Eager step: issue the all-reduce right here.  While the step is being CAPTURED into a CUDA graph no NCCL call is
+        recorded: the graph only bumps a device flag, and step() parks the all-reduce on the communication stream behind
+        a kernel that waits for that flag (NCCL stays outside the graph, the overlap stays)."""
+        st = self.eng.store
+        if torch.cuda.is_current_stream_capturing():
+            L.call("tris_flag_inc", C.c_void_p(self._flag.data_ptr()))
+            self._graph_signals = True
+            return
+        self._early_work = dist.all_reduce(st.grad[self._early_lo: st.n_train], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def _park_early_all_reduce(self):
+        """Graph mode: queue [wait for this step's flag] -> [all-reduce of everything behind the image tower] on the
+        communication stream; it fires in the middle of the replayed backward."""
+        st = self.eng.store
+        self._flag_target += 1
+        with torch.cuda.stream(self._comm):
+            L.call("tris_flag_wait", C.c_void_p(self._flag.data_ptr()), C.c_uint32(self._flag_target & 0xFFFFFFFF))
+            self._early_work = dist.all_reduce(st.grad[self._early_lo: st.n_train], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
     def optimizer_step(self):
         st = self.eng.store
-        dp.all_reduce_gradients(st.grad[: st.n_train], self.pg)   # ONE collective per step (NCCL over NVLink)
+        if self._early_work is not None:
+            self._early_work.wait()                                   # current stream waits for the overlapped part
+            self._early_work = None
+            dp.all_reduce_gradients(st.grad[: self._early_lo], self.pg)   # image-tower prefix (24 % of the payload)
+        else:
+            dp.all_reduce_gradients(st.grad[: st.n_train], self.pg)   # ONE collective per step (NCCL over NVLink)
         L.call("tris_adamw_step", C.c_void_p(st.flat.data_ptr()), C.c_void_p(st.grad.data_ptr()), C.c_void_p(self.m.data_ptr()),
                C.c_void_p(self.v.data_ptr()), C.c_void_p(st.shadow.data_ptr()), C.c_long(st.n_train),
                C.c_long(st.group_bounds[1]), C.c_void_p(self.step_count.data_ptr()), C.c_float(self.max_iter),
@@ -115,7 +162,12 @@ class Stage1Trainer:
         if s_neg is not None:
             s_neg.copy_(neg_word_ids, non_blocking=True)
         self.graph.replay()
-        if self.world > 1:            # the NCCL all-reduce + AdamW stay outside the graph in multi-rank runs
+        if self._graph_signals:
+            # multi-rank: the bulk all-reduce waits on the comm stream for the signal from inside the replay.  It is parked
+            # AFTER the replay was enqueued: a spinning kernel can stall work queued behind it on a shared hardware queue,
+            # and everything queued later (the rest of optimizer_step) depends on this all-reduce anyway.
+            self._park_early_all_reduce()
+        if not self._graph_has_optimizer:     # multi-rank: the NCCL all-reduces + AdamW follow the replayed forward/backward
             self.optimizer_step()
         # the replayed AdamW ran AFTER the replayed re-derivation of the packed operands: an eval forward that follows
         # (validate after each epoch) must re-derive them from the updated masters
@@ -137,9 +189,29 @@ class Stage1Trainer:
                 self._step_eager(s_img, s_ids, s_neg)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            out = self._step_eager(s_img, s_ids, s_neg) if self.world == 1 else self._fwd_bwd(s_img, s_ids, s_neg)
+        # multi-rank: forward+backward are captured, NCCL and AdamW run eagerly behind the replay; the bulk all-reduce is
+        # released from INSIDE the replay by a device flag (see _early_all_reduce).  TRIS_DP_GRAPH_NCCL=1 tries to capture the
+        # whole step with the NCCL calls inside the graph instead (hung on this stack when tried: off by default).
+        want_nccl_in_graph = self.world > 1 and os.environ.get("TRIS_DP_GRAPH_NCCL", "0") == "1"
+        g, out = None, None
+        if self.world == 1 or want_nccl_in_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self._step_eager(s_img, s_ids, s_neg)
+                self._graph_has_optimizer = True
+            except Exception as e:          # pragma: no cover - depends on the NCCL / driver combination
+                if self.world == 1:
+                    raise
+                print(f"[tris_b200] capturing NCCL inside the step graph failed ({e!r}); falling back to eager collectives", flush=True)
+                g = None
+                torch.cuda.synchronize()
+        if g is None:
+            self._graph_has_optimizer = False
+            self._graph_signals = False
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._fwd_bwd(s_img, s_ids, s_neg)
         self.graph, self.static = g, (s_img, s_ids, s_neg, out)
         self._restore(snap)
         return self
