@@ -322,51 +322,45 @@ def run_gpu_arm(a):
     ms_e2e = timed(e2e_step, a.steps)
     pf.take()
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit conv): one CUDA-event pair per GEMM launch of one
-    # forward+backward; side-stream overlap is off for this pass so no other kernel shares the SMs with a timed GEMM.
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM / implicit conv), measured INSIDE the step: a second copy of
+    # the whole step (same streams, same overlap) is captured into a CUDA graph in which every GEMM launch carries a
+    # time-stamp slot; the kernel itself leaves min(%globaltimer at CTA start) / max(%globaltimer at CTA end) there.  The
+    # per-launch durations therefore come from graph replays of the real step -- no profiler, no Python enqueue gaps
+    # (round 1's eager event pairs summed to more than the step itself).  FLOPs are algorithmic: 2*M*N*K*taps times the share
+    # of the call that is not zero padding (stem).
     prof = None
     if rank == 0:
-        import tris_b200.engine as E
-        saved_graph, trainer.graph = trainer.graph, None
-        saved_overlap, E.OVERLAP = E.OVERLAP, False
-        gemm_calls = []
-        orig = L.gemm_raw
-
-        def timed_gemm(desc, launches=1):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            orig(desc, launches)
-            e.record()
-            taps = desc.taps if (desc.wgrad and desc.taps > 1) else 1
-            nb = max(1, desc.batch)
-            esz = 4 if desc.out_dtype == L.DT_F32 else 2
-            if desc.a_mode == L.OP_CONV and not desc.wgrad:       # activation read once (not once per tap) + weights + output
-                by = 2.0 * desc.M * (desc.K // max(1, desc.taps)) + 2.0 * desc.N * desc.K + esz * desc.M * desc.N
-            else:
-                by = 2.0 * desc.M * desc.K * (nb if desc.a_batch_stride else 1) + 2.0 * desc.N * desc.K * (nb if desc.b_batch_stride else 1) \
-                    + esz * desc.M * desc.N * taps * nb
-            gemm_calls.append((s, e, 2.0 * desc.M * desc.N * desc.K * taps * nb, by))
-
-        L.gemm_raw = timed_gemm
-        gemm.L.gemm_raw = timed_gemm
-        # queue the whole eager pass behind a ~100 ms spin kernel so that the launches are already enqueued when the GPU
-        # reaches them: the per-launch event pairs then measure kernel durations rather than Python launch gaps
-        how = "CUDA-event pair per launch, eager fwd+bwd queued behind a 100 ms spin kernel, side-stream overlap off"
-        torch.cuda.synchronize()
+        buf = torch.empty((4096, 2), dtype=torch.int64, device="cuda")
+        saved = (trainer.graph, trainer.static, trainer._graph_has_optimizer, trainer._graph_signals)
+        gemm.timing = [buf, 0, []]
         try:
-            torch.cuda._sleep(int(2.0e8))
-        except Exception:  # pragma: no cover  (private helper; without it the figure only gets more conservative)
-            how = "CUDA-event pair per launch, eager fwd+bwd, side-stream overlap off"
-        trainer._fwd_bwd(*dev[0])
-        torch.cuda.synchronize()
-        t_ms = sum(c[0].elapsed_time(c[1]) for c in gemm_calls)
-        L.gemm_raw = orig
-        gemm.L.gemm_raw = orig
-        trainer.graph = saved_graph
-        E.OVERLAP = saved_overlap
-        fl = sum(c[2] for c in gemm_calls)
-        prof = {"launches": len(gemm_calls), "ms": t_ms, "tflops": fl / (t_ms * 1e-3) / 1e12, "gflop": fl / 1e9, "how": how,
-                "bytes": sum(c[3] for c in gemm_calls)}
+            trainer.graph = None
+            # world 1: one eager pass + the captured pass (both hand out slots in the same order).  Multi-rank: only rank 0 is
+            # here, so no warm-up step (it would all-reduce); the captured graph is forward+backward without collectives.
+            wu = 1 if world == 1 else 0
+            trainer.capture(*dev[0], warmup=wu)
+        finally:
+            slots, recs = gemm.timing[1], gemm.timing[2]
+            gemm.timing = None
+        per_pass = slots // (wu + 1)
+        recs = recs[wu * per_pass: (wu + 1) * per_pass]
+        sums, spans = [], []
+        for _ in range(3):
+            buf[:, 0] = torch.iinfo(torch.int64).max
+            buf[:, 1] = 0
+            trainer.graph.replay()                 # the stamped graph (static inputs = batch 0)
+            torch.cuda.synchronize()
+            sl = buf[wu * per_pass: (wu + 1) * per_pass].cpu()
+            sums.append((sl[:, 1] - sl[:, 0]).clamp(min=0).double().sum().item() * 1e-6)
+            spans.append((sl[:, 1].max() - sl[:, 0].min()).item() * 1e-6)
+        t_ms = statistics.median(sums)
+        fl = sum(r[0] for r in recs)
+        prof = {"launches": per_pass, "ms": t_ms, "tflops": fl / (t_ms * 1e-3) / 1e12, "gflop": fl / 1e9,
+                "how": "device time stamps (%globaltimer: min over CTA starts, max over CTA ends) left by every GEMM launch inside "
+                       "CUDA-graph replays of the whole overlapped step; sum over the launches of one step, median of 3 replays",
+                "bytes": sum(r[2] for r in recs), "gflop_issued": sum(r[1] for r in recs) / 1e9,
+                "span_ms": statistics.median(spans)}
+        trainer.graph, trainer.static, trainer._graph_has_optimizer, trainer._graph_signals = saved
 
     # ---- cross-modal attention group (K6 tail + K7 + K8: north-star "attn HBM GB/s"): forward of the head on resident
     # c4 / hidden, one CUDA-event pair per repetition, L2 flushed (256 MB write) between repetitions
@@ -398,7 +392,7 @@ def run_gpu_arm(a):
         return
     sust, burst, hbm, src = peaks()
     traffic = share_ncu = None
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
     if os.path.exists(tpath) and B == 48:
         tj = json.load(open(tpath))
         traffic = tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]
@@ -427,10 +421,11 @@ def run_gpu_arm(a):
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": prof["tflops"], "peak": sust, "unit": "TFLOP/s", "frac": prof["tflops"] / sust,
-                     "traffic": traffic, "traffic_unit": "bytes per step (all GEMM launches, ncu dram__bytes_read+write, profiles/r1_gemm_traffic.json)",
+                     "traffic": traffic, "traffic_unit": "bytes per step (all GEMM launches, ncu dram__bytes_read+write, profiles/r2_gemm_traffic.json)",
                      "algorithmic_bytes": prof["bytes"],
                      "kernel": "tris_umma_gemm_kernel", "peak_source": f"{src} sustained bf16", "timing": prof["how"],
                      "launches_per_step": prof["launches"], "kernel_ms_per_step": prof["ms"], "kernel_gflop_per_step": prof["gflop"],
+                     "kernel_gflop_issued_per_step": prof["gflop_issued"], "first_to_last_gemm_ms": prof["span_ms"],
                      "kernel_share_of_step_ncu": share_ncu,
                      "step_frac_of_peak": (GFLOP_PER_SAMPLE * 1e9 * sps / world) / (sust * 1e12)},
         "cross_modal_attention": k7,

@@ -95,6 +95,9 @@ typedef struct tris_gemm_desc {
     int32_t defer_reduce; /* 1 = split-K: only store the partials; the caller reduces them later, many tensors per launch, with
                              tris_splitk_reduce_multi (rows = M, w = W, split = the effective split this call reports back) */
     int32_t split_used;   /* OUT: effective split count of this call (<= split_k) */
+    uint64_t* tstamp;     /* optional uint64[2], initialised {UINT64_MAX, 0}: the kernel leaves min(%globaltimer at CTA start)
+                             and max(%globaltimer at CTA end) there -- the device-side duration of this launch, also inside
+                             a CUDA-graph replay (measurement aid of bench.py; NULL in production) */
 } tris_gemm_desc;
 
 int tris_gemm(tris_gemm_desc* desc, tris_stream_t stream);

@@ -65,6 +65,7 @@ struct KParams {
     const float* mask_sc;            // optional [N]: multiply the output by ((stats_y * mask_sc + mask_sh) > 0)  (ReLU mask
     const float* mask_sh;            //   of relu(bn(y)) recomputed from y)
     int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
+    unsigned long long* tstamp;      // optional [2]: min(%globaltimer at CTA start), max(%globaltimer at CTA end) of this launch
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
     int ldd, act, out_f32, atomic;
@@ -148,6 +149,11 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k * p.batch;
 
     if (threadIdx.x == 0) {
+        if (p.tstamp != nullptr) {   // measurement aid (bench.py): device-side start of this launch
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMin(p.tstamp, t);
+        }
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_b);
         ptx::prefetch_tmap(&map_d);
@@ -587,6 +593,11 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (p.tstamp != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(p.tstamp + 1, t);
+    }
 }
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -797,6 +808,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.stats_parts = g->stats_parts; p.stats_mode = g->stats_mode;
     p.stats_y = reinterpret_cast<const __nv_bfloat16*>(g->stats_y); p.stats_mu = g->stats_mu;
     p.mask_sc = g->mask_sc; p.mask_sh = g->mask_sh;
+    p.tstamp = reinterpret_cast<unsigned long long*>(g->tstamp);
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;

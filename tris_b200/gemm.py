@@ -40,7 +40,32 @@ def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
 WGRAD_MAX_CTAS = int(os.environ.get("TRIS_WGRAD_CTAS", "0"))   # experiment: cap the SMs a side-stream weight gradient takes
 
 
+# Share of a GEMM call's 2*M*N*K that is algorithmic work (bench.py's roofline counts un-padded FLOPs): the stem convs
+# run with zero-padded / block-diagonal operands (27 -> 64 im2col columns, image-pair packing), see resnet.py.
+algo_share = 1.0
+
+
+class algo(object):
+    """with algo(0.5): ... -- tags the GEMM calls inside with their algorithmic share (read by bench.py only)."""
+
+    def __init__(self, share):
+        self.share = share
+
+    def __enter__(self):
+        global algo_share
+        self.prev, algo_share = algo_share, self.share
+
+    def __exit__(self, *a):
+        global algo_share
+        algo_share = self.prev
+
+
 STAT_PARTS = 148   # rows of a partial-statistics buffer (ops.STAT_PARTS): one per CTA of the persistent kernel
+
+
+# bench.py's kernel timing: when set to [uint64 tensor [n, 2], next slot, records], every GEMM launch gets a time-stamp slot
+# (the kernel writes its device-side start / end there) and a record (algorithmic flops, issued flops, bytes)
+timing = None
 
 
 def _desc(**kw) -> L.GemmDesc:
@@ -49,6 +74,19 @@ def _desc(**kw) -> L.GemmDesc:
         setattr(d, k, v)
     if d.stats:
         d.stats_parts = STAT_PARTS
+    if timing is not None and timing[1] < timing[0].shape[0]:
+        d.tstamp = timing[0].data_ptr() + 16 * timing[1]
+        timing[1] += 1
+        taps = d.taps if (d.wgrad and d.taps > 1) else 1
+        nb = max(1, d.batch)
+        full = 2.0 * d.M * d.N * d.K * taps * nb
+        esz = 4 if d.out_dtype == L.DT_F32 else 2
+        if d.a_mode == L.OP_CONV and not d.wgrad:       # activation read once (not once per tap) + weights + output
+            by = 2.0 * d.M * (d.K // max(1, d.taps)) + 2.0 * d.N * d.K + esz * d.M * d.N
+        else:
+            by = 2.0 * d.M * d.K * (nb if d.a_batch_stride else 1) + 2.0 * d.N * d.K * (nb if d.b_batch_stride else 1) \
+                + esz * d.M * d.N * taps * nb
+        timing[2].append((full * algo_share, full, by))
     return d
 
 

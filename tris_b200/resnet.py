@@ -198,13 +198,16 @@ class ResNetTower:
         B2 = B // 2
         col = ops.stem_im2col_pair(img.contiguous())
         s = stats(64)
-        y1 = G.linear_fwd(col, self.w_pair1, stats=s).view(B2, H // 2, W // 2, 64)
+        with G.algo(27 * 32 / (64 * 32)):                  # block-diagonal [2 x (27 -> 32)] inside a 64 x 64 GEMM
+            y1 = G.linear_fwd(col, self.w_pair1, stats=s).view(B2, H // 2, W // 2, 64)
         a1 = ops.bn_apply(y1, s, self.pair_bn[p + "bn1"], train, fold_half=32 if train else 0)
         s2 = stats(64)
-        y2 = G.conv3x3_fwd(a1, self.w_pair2, stats=s2)
+        with G.algo(0.5):                                  # block-diagonal pair packing: half of the MACs are zeros
+            y2 = G.conv3x3_fwd(a1, self.w_pair2, stats=s2)
         a2 = ops.bn_apply(y2, s2, self.pair_bn[p + "bn2"], train, fold_half=32 if train else 0)
         s3 = stats(128)
-        y3 = G.conv3x3_fwd(a2, self.w_pair3, stats=s3)
+        with G.algo(0.5):
+            y3 = G.conv3x3_fwd(a2, self.w_pair3, stats=s3)
         xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2, fold_half=64 if train else 0)   # [B/2, H/4, W/4, 128]
         x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64).contiguous()   # un-pair: layout only
         if train:
@@ -356,15 +359,18 @@ class ResNetTower:
         dy3, _, _ = ops.bn_bwd(dxp, None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64)
         self._wgrad3x3_pair(dy3, a2, p + "conv3.weight")
         ext2, bs2 = self._bwd_stats(y2, self.pair_bn[p + "bn2"]) if FUSE_BN_BWD else (None, None)
-        da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64, bwd_stats=bs2)
+        with G.algo(0.5):
+            da2 = G.conv3x3_dgrad(dy3, self.w_pair3, 64, bwd_stats=bs2)
         dy2, _, _ = ops.bn_bwd(da2, None, y2, self.pair_bn[p + "bn2"], fold_half=32, ext=ext2)
         self._wgrad3x3_pair(dy2, a1, p + "conv2.weight")
         ext1, bs1 = self._bwd_stats(y1, self.pair_bn[p + "bn1"]) if FUSE_BN_BWD else (None, None)
-        da1 = G.conv3x3_dgrad(dy2, self.w_pair2, 64, bwd_stats=bs1)
+        with G.algo(0.5):
+            da1 = G.conv3x3_dgrad(dy2, self.w_pair2, 64, bwd_stats=bs1)
         dy1, _, _ = ops.bn_bwd(da1, None, y1, self.pair_bn[p + "bn1"], fold_half=32, ext=ext1)
 
         def stem1():
-            gw = G.linear_wgrad(dy1.view(-1, 64), col, queue=self._wgq)   # [64, 64] fp32, two diagonal 32 x 27 blocks
+            with G.algo(27 * 32 / (64 * 32)):
+                gw = G.linear_wgrad(dy1.view(-1, 64), col, queue=self._wgq)   # [64, 64] fp32, two diagonal 32 x 27 blocks
             g1 = st.g(p + "conv1.weight")
             self._post(lambda: g1.add_((gw[:32, :27] + gw[32:, 32:59]).reshape(32, 3, 3, 3).permute(0, 3, 1, 2)))
         self._wg(stem1, dy1, col)
@@ -378,7 +384,8 @@ class ResNetTower:
         gw = self.store.g(key)
 
         def run():
-            gp = G.conv3x3_wgrad(dy, x, queue=self._wgq)
+            with G.algo(0.5):
+                gp = G.conv3x3_wgrad(dy, x, queue=self._wgq)
             self._post(lambda: ops.unpack_conv_grad_blockdiag(gp, gw, 2))
         self._wg(run, dy, x)
 
