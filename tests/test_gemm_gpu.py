@@ -218,3 +218,13 @@ def test_weight_gradients_are_bit_reproducible(G):
     s1 = st.clone()
     G.linear_fwd(dy, w, stats=st)
     assert torch.equal(s1, st) and torch.equal(o1, G.linear_fwd(dy, w, stats=st))
+
+
+def test_dgrad_with_bit_masked_residual(G):
+    """dx = dy W + r * bit: the residual join of a bottleneck in backward without materialising the masked gradient."""
+    m, n, k = 4800, 256, 1024
+    dy, w, r = rnd(m, n, seed=1), rnd(n, k, seed=2, scale=n ** -0.5), rnd(m, k, seed=3)
+    keep = torch.rand(m, k, device="cuda") > 0.4
+    bits = (keep.reshape(m, k // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(-1).to(torch.uint8)
+    out = G.linear_dgrad(dy, w, residual=r, res_bits=bits.contiguous())
+    assert rel(out, dy.float() @ w.float() + r.float() * keep) < 1e-2

@@ -98,6 +98,20 @@ def test_bn_apply_and_backward(K, c, pool, mode):
         assert rel(bn1.dgamma, grads[4]) < 1e-2 and rel(bn1.dbeta, grads[5]) < 1e-2
     if mode == "residual":
         assert rel(gid, dout.float() * (out.float() > 0)) < 1e-2
+    if mode != "plain" and pool == 1:
+        # the sign-bit mask written by the forward kernel replaces re-reading `out`: identical results, bit for bit
+        bits = torch.zeros((n * h * w, c // 8), device="cuda", dtype=torch.uint8)
+        bn_b, bn1_b = make_bn(K, c, 2), (make_bn(K, c, 4) if mode == "dual" else None)
+        out_b = K.bn_apply(y, stats_of(y), bn_b, True, relu=True, pool=pool, y1=y1, stats1=stats_of(y1) if y1 is not None else None,
+                           bn1=bn1_b, residual=res, bits=bits)
+        assert torch.equal(out_b, out)
+        want = (out.float().reshape(n * h * w, c // 8, 8) > 0).to(torch.uint8)
+        want = (want << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(-1).to(torch.uint8)
+        assert torch.equal(bits, want)
+        dy_b, dy1_b, _ = K.bn_bwd(dout, None, y, bn_b, relu=True, pool=pool, y1=y1, bn1=bn1_b, bits=bits)
+        assert torch.equal(dy_b, dy) and torch.equal(bn_b.dgamma, bn.dgamma) and torch.equal(bn_b.dbeta, bn.dbeta)
+        if mode == "dual":
+            assert torch.equal(dy1_b, dy1)
 
 
 def test_bn_eval_mode(K):

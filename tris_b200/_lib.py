@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ("stats_y", C.c_void_p), ("stats_mu", C.c_void_p), ("mask_sc", C.c_void_p), ("mask_sh", C.c_void_p),
         ("splitk_ws", C.c_void_p),
         ("defer_reduce", C.c_int32), ("split_used", C.c_int32),
-        ("tstamp", C.c_void_p),
+        ("res_bits", C.c_void_p), ("tstamp", C.c_void_p),
     ]
 
 

@@ -78,6 +78,8 @@ struct ApplyParams {
     BnBranch b0, b1;          // b1.y == nullptr -> single branch
     const __nv_bfloat16* residual;  // [M_out, C] or nullptr
     __nv_bfloat16* out;       // [M_out, C]
+    unsigned char* relu_bits; // optional [M_out, C/8]: bit i of byte (row, c/8) = (out[row, c + i] > 0); lets the backward
+                              // kernels mask the upstream gradient without re-reading the bf16 output (1/16 of its bytes)
     int n, h, w, c, pool, relu, train;
     float count, momentum, eps;
 };
@@ -130,6 +132,16 @@ __device__ __forceinline__ float fin_partial(const float* base, int nrows, long 
     return s;
 }
 template <int G>
+__device__ __forceinline__ float2 fin_combine2(float2 (*sm)[33], float2 v) {
+    __syncthreads();
+    sm[threadIdx.x >> 5][threadIdx.x & 31] = v;
+    __syncthreads();
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < G; ++g) { const float2 x = sm[g][threadIdx.x & 31]; t.x += x.x; t.y += x.y; }
+    return t;
+}
+template <int G>
 __device__ __forceinline__ float fin_combine(float (*sm)[33], float v) {
     __syncthreads();
     sm[threadIdx.x >> 5][threadIdx.x & 31] = v;
@@ -140,47 +152,54 @@ __device__ __forceinline__ float fin_combine(float (*sm)[33], float v) {
     return t;
 }
 
-__device__ void bn_fwd_finalize_group(const FinalizeParams& p, int br, int group, float (*sm)[33]) {
+__device__ void bn_fwd_finalize_group(const FinalizeParams& p, int br, int group, float2 (*sm)[33]) {
     const int c = group * 32 + (threadIdx.x & 31);
     const int cc = c < p.c ? c : p.c - 1;                       // tail lanes shadow a valid column (no divergence at the barriers)
     const long rs = 2L * p.c;
     const float* parts = p.parts[br];
+    // parameters first: their latency hides behind the partial-row loads
+    float gam = 0.f, bet = 0.f, rm = 0.f, rv = 0.f;
+    const bool writer = c < p.c && threadIdx.x < 32;
+    if (writer) {
+        if (p.scale[br] != nullptr) { gam = __ldg(p.gamma[br] + c); bet = __ldg(p.beta[br] + c); }
+        if (p.rm[br] != nullptr) { rm = p.rm[br][c]; rv = p.rv[br][c]; }
+    }
     float s, q;
     if (p.fold_half > 0) {
         const int lo = cc < p.fold_half ? cc : cc - p.fold_half, hi = lo + p.fold_half;
-        const float ps0 = fin_partial<kFinGroups>(parts + lo, p.nparts, rs), ps1 = fin_partial<kFinGroups>(parts + hi, p.nparts, rs);
-        const float pq0 = fin_partial<kFinGroups>(parts + p.c + lo, p.nparts, rs), pq1 = fin_partial<kFinGroups>(parts + p.c + hi, p.nparts, rs);
-        const float s0 = fin_combine<kFinGroups>(sm, ps0), s1 = fin_combine<kFinGroups>(sm, ps1);
-        const float q0 = fin_combine<kFinGroups>(sm, pq0), q1 = fin_combine<kFinGroups>(sm, pq1);
-        s = (s0 + s1) * 0.5f;
-        q = (q0 + q1) * 0.5f;
+        const float2 p0 = make_float2(fin_partial<kFinGroups>(parts + lo, p.nparts, rs), fin_partial<kFinGroups>(parts + p.c + lo, p.nparts, rs));
+        const float2 p1 = make_float2(fin_partial<kFinGroups>(parts + hi, p.nparts, rs), fin_partial<kFinGroups>(parts + p.c + hi, p.nparts, rs));
+        const float2 t0 = fin_combine2<kFinGroups>(sm, p0), t1 = fin_combine2<kFinGroups>(sm, p1);
+        s = (t0.x + t1.x) * 0.5f;
+        q = (t0.y + t1.y) * 0.5f;
     } else {
-        const float ps = fin_partial<kFinGroups>(parts + cc, p.nparts, rs), pq = fin_partial<kFinGroups>(parts + p.c + cc, p.nparts, rs);
-        s = fin_combine<kFinGroups>(sm, ps);
-        q = fin_combine<kFinGroups>(sm, pq);
+        const float2 t = fin_combine2<kFinGroups>(sm, make_float2(fin_partial<kFinGroups>(parts + cc, p.nparts, rs),
+                                                                  fin_partial<kFinGroups>(parts + p.c + cc, p.nparts, rs)));
+        s = t.x;
+        q = t.y;
     }
-    if (c >= p.c || threadIdx.x >= 32) return;
+    if (!writer) return;
     const float mean = s / p.count;
     const float var = fmaxf(q / p.count - mean * mean, 0.f);
     const float invstd = rsqrtf(var + p.eps);
     p.mean[br][c] = mean;
     p.invstd[br][c] = invstd;
     if (p.scale[br] != nullptr) {
-        const float sc = p.gamma[br][c] * invstd;
+        const float sc = gam * invstd;
         p.scale[br][c] = sc;
-        p.shift[br][c] = p.beta[br][c] - mean * sc;
+        p.shift[br][c] = bet - mean * sc;
     }
     if (p.rm[br] != nullptr) {
         const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
-        p.rm[br][c] = (1.f - p.momentum) * p.rm[br][c] + p.momentum * mean;
-        p.rv[br][c] = (1.f - p.momentum) * p.rv[br][c] + p.momentum * unbiased;
+        p.rm[br][c] = (1.f - p.momentum) * rm + p.momentum * mean;
+        p.rv[br][c] = (1.f - p.momentum) * rv + p.momentum * unbiased;
     }
 }
 
 // (Folding this step into the head of the apply kernel behind an in-kernel counter was measured SLOWER, 20.0 vs 19.0 ms per
 // step: every CTA of the apply grid then pays same-address atomics for the ticket / exit protocol.  It stays a tiny kernel.)
 __global__ void __launch_bounds__(32 * kFinGroups) bn_fwd_finalize_kernel(const FinalizeParams p) {
-    __shared__ float sm[kFinGroups][33];
+    __shared__ float2 sm[kFinGroups][33];
     pdl_wait();                    // the conv GEMM that wrote the partial rows
     pdl_launch_dependents();       // the apply kernel may be set up now (it waits for this grid itself)
     bn_fwd_finalize_group(p, blockIdx.y, blockIdx.x, sm);
@@ -253,6 +272,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
                 }
         }
         st8(p.out + orow * p.c + c0, acc);
+        if (p.relu_bits != nullptr) {
+            unsigned b = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b |= (acc.v[i] > 0.f ? 1u : 0u) << i;
+            p.relu_bits[orow * (p.c >> 3) + (c0 >> 3)] = static_cast<unsigned char>(b);
+        }
     }
 }
 
@@ -260,6 +285,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
 struct BwdParams {
     const __nv_bfloat16* dout;   // [M_out, C]
     const __nv_bfloat16* out;    // [M_out, C] forward output (relu mask source) or nullptr -> recompute from y0
+    const unsigned char* relu_bits;   // [M_out, C/8] sign bits of the forward output (preferred over `out`: 1/16 of the bytes)
     BnBranch b0, b1;             // y, gamma, beta, save_mean, save_invstd are inputs here
     float* dgamma0; float* dbeta0; float* dgamma1; float* dbeta1;   // [C] fp32 gradient buffers (+= by the finalize kernel)
     float* parts;                // [nparts][K][C] per-CTA partial sums: k = 0 sum g, 1 sum g (y0 - mu0), 2 sum g (y1 - mu1)
@@ -289,7 +315,11 @@ __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long orow, int c
         for (int i = 0; i < 8; ++i) g.v[i] *= 0.25f;
     }
     if (p.relu) {
-        if (p.out != nullptr) {
+        if (p.relu_bits != nullptr) {
+            const unsigned b = __ldg(p.relu_bits + orow * (p.c >> 3) + (c0 >> 3));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g.v[i] = ((b >> i) & 1u) ? g.v[i] : 0.f;
+        } else if (p.out != nullptr) {
             Vec8 o = ld8(p.out + orow * p.c + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) g.v[i] = o.v[i] > 0.f ? g.v[i] : 0.f;
@@ -545,7 +575,7 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
                       const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1,
                       const void* residual, void* out, int n, int h, int w, int c, int pool, int relu, int train,
                       float momentum, float eps, int stats_parts, int fold_half, float* save_scale0, float* save_shift0,
-                      tris_stream_t stream) {
+                      void* relu_bits, tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_apply_fwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pool must be 1 or 2");
     if (pool == 2 && (y1 || residual || (h & 1) || (w & 1))) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pooled form is single-branch, even h/w");
@@ -557,6 +587,8 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
     p.b1 = {reinterpret_cast<const __nv_bfloat16*>(y1), stats1, gamma1, beta1, rm1, rv1, save_mean1, save_invstd1};
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.relu_bits = reinterpret_cast<unsigned char*>(relu_bits);
+    if (relu_bits && (pool != 1 || !relu)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: relu_bits needs relu, pool 1");
     p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = relu; p.train = train;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     p.momentum = momentum; p.eps = eps;
@@ -592,7 +624,7 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
                 const void* y1, const float* gamma1, const float* beta1, const float* save_mean1,
                 const float* save_invstd1, float* dgamma1, float* dbeta1, void* dy1, void* g_out, int n, int h, int w,
                 int c, int pool, int relu, int fold_half, float* ws, long ws_floats, int ext_parts,
-                tris_stream_t stream) {
+                const void* relu_bits, tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_bwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: pool must be 1 or 2");
     if (!ws) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: workspace required");
@@ -601,6 +633,8 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     BwdParams p{};
     p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
     p.out = reinterpret_cast<const __nv_bfloat16*>(out);
+    p.relu_bits = reinterpret_cast<const unsigned char*>(relu_bits);
+    if (relu_bits && pool != 1) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: relu_bits is for the un-pooled form");
     p.b0 = {reinterpret_cast<const __nv_bfloat16*>(y0), nullptr, gamma0, beta0, nullptr, nullptr,
             const_cast<float*>(save_mean0), const_cast<float*>(save_invstd0)};
     p.b1 = {reinterpret_cast<const __nv_bfloat16*>(y1), nullptr, gamma1, beta1, nullptr, nullptr,

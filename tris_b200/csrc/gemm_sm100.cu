@@ -65,6 +65,7 @@ struct KParams {
     const float* mask_sc;            // optional [N]: multiply the output by ((stats_y * mask_sc + mask_sh) > 0)  (ReLU mask
     const float* mask_sh;            //   of relu(bn(y)) recomputed from y)
     int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
+    const unsigned char* res_bits;   // optional [M, N/8]: residual added only where its bit is set
     unsigned long long* tstamp;      // optional [2]: min(%globaltimer at CTA start), max(%globaltimer at CTA end) of this launch
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
@@ -415,6 +416,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 auto add_residual = [&]() {
                     if (p.residual != nullptr && rvalid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+                        uint32_t bits = 0xffffffffu;
+                        if (p.res_bits != nullptr) bits = __ldg(reinterpret_cast<const uint32_t*>(p.res_bits + grow * (p.N >> 3) + (ncol0 >> 3)));
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             if (ncol0 + g * 8 < p.N) {
@@ -423,8 +426,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     float2 f = __bfloat1622float2(r2[j]);
-                                    v[g * 8 + 2 * j] += f.x;
-                                    v[g * 8 + 2 * j + 1] += f.y;
+                                    v[g * 8 + 2 * j] += ((bits >> (g * 8 + 2 * j)) & 1u) ? f.x : 0.f;
+                                    v[g * 8 + 2 * j + 1] += ((bits >> (g * 8 + 2 * j + 1)) & 1u) ? f.y : 0.f;
                                 }
                             }
                         }
@@ -481,7 +484,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             ptx::named_bar_sync(1, 256);
             // ---- TMA store (one elected thread), issued BEFORE the statistics pass: both only read the staged tile, so the
             // store drains while the epilogue warps accumulate the column sums
-            if (ew == 0 && !(p.dbg & 4) && ptx::elect_one()) {
+            if (ew == 0 && !(p.dbg & (4 | 64)) && ptx::elect_one()) {
                 for (int g = 0; g < ngroups; ++g) {
                     const int cg = n0 + g * gw;
                     if (cg >= p.N) break;
@@ -507,7 +510,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // ---- BatchNorm column statistics of the stored (bf16-rounded) tile.  Thread = (16-byte vector of 8 columns,
             // row part): one LDS.128 + 3 instructions per element; parts are combined through a 16 KB scratch and the
             // per-CTA totals live in smem until the kernel ends (one global atomic per column per CTA).
-            if (p.stats != nullptr && !(p.dbg & 4)) {
+            if (p.stats != nullptr && !(p.dbg & (4 | 32))) {
                 int rlim = kBlockM;
                 constexpr bool conv_tile = (AM == LD_CONV);
                 if (conv_tile) rlim = p.th * p.tw;
@@ -809,6 +812,8 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.stats_y = reinterpret_cast<const __nv_bfloat16*>(g->stats_y); p.stats_mu = g->stats_mu;
     p.mask_sc = g->mask_sc; p.mask_sh = g->mask_sh;
     p.tstamp = reinterpret_cast<unsigned long long*>(g->tstamp);
+    p.res_bits = reinterpret_cast<const unsigned char*>(g->res_bits);
+    if (g->res_bits && (!g->residual || g->N % 32 || batch > 1 || conv)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: res_bits needs a residual, N %% 32 == 0, plain 2-D mode");
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;

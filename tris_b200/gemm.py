@@ -166,7 +166,7 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
 
 
 def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None, dact_src=None,
-                 act=L.ACT_NONE, bias=None, bwd_stats=None):
+                 act=L.ACT_NONE, bias=None, bwd_stats=None, res_bits=None):
     """dx[M,K] = dy[M,N] @ w[N,K]   (w read MN-major: no transposed weight copy)."""
     _chk(dy, torch.bfloat16, "dy"); _chk(w, torch.bfloat16, "w")
     m, n = dy.shape
@@ -180,7 +180,8 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
         bn = min(bn, 128)
     d = _desc(**_bwd_stats(dict(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
               b_mode=L.OP_MN2D, M=m, N=k, K=n, lda=n, ldb=k, ldd=k, taps=1, block_n=bn, split_k=1, act=act,
-              dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16), bwd_stats))
+              dact_src=L.ptr(dact_src), out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16,
+              res_bits=L.ptr(res_bits)), bwd_stats))
     L.gemm_raw(d)
     return out
 

@@ -230,14 +230,16 @@ class ResNetTower:
         s3 = stats(4 * pl)
         y3 = G.linear_fwd(a2.view(-1, pl), self._w1x1(q + "conv3.weight"), stats=s3).view(B, Ho, Wo, 4 * pl)
         xp = yd = None
+        # sign bits of the block output: the ReLU mask of the residual join for the backward pass (1/16 of the bytes of `out`)
+        bits = torch.empty((B * Ho * Wo, pl // 2), device=x.device, dtype=torch.uint8) if train else None
         if blk.down:
             xp = ops.avgpool2(x) if blk.stride > 1 else x
             sd = stats(4 * pl)
             yd = G.linear_fwd(xp.view(-1, Cin), self._w1x1(q + "downsample.0.weight"), stats=sd).view(B, Ho, Wo, 4 * pl)
-            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, y1=yd, stats1=sd, bn1=self.bn[q + "downsample.1"])
+            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, y1=yd, stats1=sd, bn1=self.bn[q + "downsample.1"], bits=bits)
         else:
-            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, residual=x)
-        return out, ((x, y1, a1, y2, a2, y3, xp, yd, out) if train else None)
+            out = ops.bn_apply(y3, s3, self.bn[q + "bn3"], train, residual=x, bits=bits)
+        return out, ((x, y1, a1, y2, a2, y3, xp, yd, bits) if train else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, tape, dout: torch.Tensor):
@@ -405,15 +407,17 @@ class ResNetTower:
     def _block_bwd(self, blk: _Block, rec, dout, ext=None, prev=None, prev_rec=None):
         """-> (dx, ext_prev).  ext: fused partial sums of this block's bn3 (then `dout` is the masked gradient g).
         prev / prev_rec: the block in front, when this block's input-gradient GEMM is to fuse ITS bn3 reduction."""
-        x, y1, a1, y2, a2, y3, xp, yd, out = rec
+        x, y1, a1, y2, a2, y3, xp, yd, bits = rec
         q, pl = blk.p, blk.planes
         Cin = x.shape[3]
+        g_bits = None          # non-None: the identity-branch gradient is `dout` masked by these bits (never materialised)
         if blk.down:
-            dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], y1=yd, bn1=self.bn[q + "downsample.1"])
+            dy3, dyd, g = ops.bn_bwd(dout, None, y3, self.bn[q + "bn3"], y1=yd, bn1=self.bn[q + "downsample.1"], bits=bits)
         elif ext is not None:
             dy3, dyd, g = ops.bn_bwd(dout, None, y3, self.bn[q + "bn3"], ext=ext)[0], None, dout
         else:
-            dy3, dyd, g = ops.bn_bwd(dout, out, y3, self.bn[q + "bn3"], want_g=True)
+            dy3, dyd, g = ops.bn_bwd(dout, None, y3, self.bn[q + "bn3"], bits=bits)[0], None, dout
+            g_bits = bits
         self._wgrad1x1(dy3.view(-1, 4 * pl), a2.view(-1, pl), q + "conv3.weight")
         ext2, bs2 = self._bwd_stats(y2, self.bn[q + "bn2"]) if (FUSE_BN_BWD and blk.stride == 1) else (None, None)
         da2 = G.linear_dgrad(dy3.view(-1, 4 * pl), self._w1x1(q + "conv3.weight"), bwd_stats=bs2).view(a2.shape)
@@ -438,7 +442,7 @@ class ResNetTower:
             # partial sums (sum g', sum g' (y3' - mean')) of the previous block's bn3 backward
             extp, bsp = self._bwd_stats(prev_rec[5], self.bn[prev.p + "bn3"], mask=False)
             dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin), dact_src=x.view(-1, Cin), act=ops.L.ACT_RELU,
-                                bwd_stats=bsp).view(x.shape)
+                                bwd_stats=bsp, res_bits=g_bits).view(x.shape)
             return dx, extp
-        dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin)).view(x.shape)
+        dx = G.linear_dgrad(dy1.view(-1, pl), w1, residual=g.view(-1, Cin), res_bits=g_bits).view(x.shape)
         return dx, None
