@@ -95,6 +95,15 @@ typedef struct tris_gemm_desc {
     int32_t defer_reduce; /* 1 = split-K: only store the partials; the caller reduces them later, many tensors per launch, with
                              tris_splitk_reduce_multi (rows = M, w = W, split = the effective split this call reports back) */
     int32_t split_used;   /* OUT: effective split count of this call (<= split_k) */
+    void* d_norm;         /* optional bf16, same shape as d: tile-local InstanceNorm epilogue (batched K-major form, M <= 128 rows
+                             per batch entry = the pixels of one image; model/attn.py:75-105).  d receives the raw product
+                             (saved for backward), d_norm = in_mix * act(IN(d) * in_gamma + in_beta) [+ in_add], with the
+                             per-(image, channel) mean / invstd written to in_mean / in_invstd [batch, N] */
+    const float* in_gamma; const float* in_beta;
+    float* in_mean; float* in_invstd;
+    const void* in_add;   /* optional bf16 [batch*M, ldd] */
+    float in_eps, in_mix; /* in_mix 0 is read as 1 */
+    int32_t in_relu;
     const void* res_bits; /* optional uint8 [M, N/8] (N % 32 == 0): the residual is added only where its bit is set -- the residual
                              join of a bottleneck in backward: dx = dy1 W1 + dout * [out > 0] without materialising the masked
                              gradient (bits from tris_bn_apply_fwd) */

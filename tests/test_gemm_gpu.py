@@ -228,3 +228,31 @@ def test_dgrad_with_bit_masked_residual(G):
     bits = (keep.reshape(m, k // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(-1).to(torch.uint8)
     out = G.linear_dgrad(dy, w, residual=r, res_bits=bits.contiguous())
     assert rel(out, dy.float() @ w.float() + r.float() * keep) < 1e-2
+
+
+@pytest.mark.parametrize("B,P,k,n,relu,mix", [(48, 100, 1024, 3072, True, 1.0), (48, 100, 1024, 1024, False, 0.1), (5, 49, 256, 192, True, 1.0),
+                                               (3, 128, 128, 64, False, 0.5)])
+def test_linear_instancenorm_fused(G, B, P, k, n, relu, mix):
+    """1x1 conv + InstanceNorm2d(affine) [+ ReLU] [* mix + add] in one batched GEMM with a tile-local epilogue
+    (v_proj / v_output of model/attn.py:75-105) against torch on the same bf16-rounded operands."""
+    x, w = rnd(B * P, k, seed=1), rnd(n, k, seed=2, scale=k ** -0.5)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    gamma = torch.rand(n, generator=g, device="cuda") + 0.5
+    beta = torch.randn(n, generator=g, device="cuda") * 0.2
+    add = rnd(B * P, n, seed=4) if not relu else None
+    y, yn, mean, invstd = G.linear_in_fwd(x, w, B, gamma, beta, relu, mix_scale=mix, mix_add=add)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t())
+    assert rel(y, ref) < 1e-2
+    yb = y.float().reshape(B, P, n)                     # statistics of the stored (bf16) values, like the unfused kernels
+    mu = yb.mean(1)
+    var = yb.var(1, unbiased=False)
+    assert rel(mean, mu) < 2e-3 or (mean - mu).abs().max() < 2e-3
+    assert rel(invstd, (var + 1e-5).rsqrt()) < 2e-3
+    o = (yb - mu[:, None]) * (var + 1e-5).rsqrt()[:, None] * gamma + beta
+    if relu:
+        o = torch.relu(o)
+    o = o * mix
+    if add is not None:
+        o = o + add.float().reshape(B, P, n)
+    assert rel(yn, o.reshape(B * P, n)) < 1e-2

@@ -37,6 +37,8 @@ class GemmDesc(C.Structure):
         ("stats_y", C.c_void_p), ("stats_mu", C.c_void_p), ("mask_sc", C.c_void_p), ("mask_sh", C.c_void_p),
         ("splitk_ws", C.c_void_p),
         ("defer_reduce", C.c_int32), ("split_used", C.c_int32),
+        ("d_norm", C.c_void_p), ("in_gamma", C.c_void_p), ("in_beta", C.c_void_p), ("in_mean", C.c_void_p), ("in_invstd", C.c_void_p),
+        ("in_add", C.c_void_p), ("in_eps", C.c_float), ("in_mix", C.c_float), ("in_relu", C.c_int32),
         ("res_bits", C.c_void_p), ("tstamp", C.c_void_p),
     ]
 

@@ -66,6 +66,12 @@ struct KParams {
     const float* mask_sh;            //   of relu(bn(y)) recomputed from y)
     int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
     const unsigned char* res_bits;   // optional [M, N/8]: residual added only where its bit is set
+    // EPI 2 (tile-local InstanceNorm: batched mode, one tile = the M <= 128 pixels of one image x bn channels)
+    const float* in_gamma; const float* in_beta;   // [N]
+    float* in_mean; float* in_invstd;               // [batch, N] saved for the backward pass
+    const __nv_bfloat16* in_add;                    // optional bf16 [batch*M, ldd]: added after the mix scale
+    float in_eps, in_mix;
+    int in_relu;
     unsigned long long* tstamp;      // optional [2]: min(%globaltimer at CTA start), max(%globaltimer at CTA end) of this launch
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
@@ -137,7 +143,7 @@ template <int AM, int BM, int EPI>
 #endif
 __global__ void __maxnreg__(TRIS_GEMM_MAXNREG)
 tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_d, const KParams p) {
+                      const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_e, const KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -510,7 +516,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // ---- BatchNorm column statistics of the stored (bf16-rounded) tile.  Thread = (16-byte vector of 8 columns,
             // row part): one LDS.128 + 3 instructions per element; parts are combined through a 16 KB scratch and the
             // per-CTA totals live in smem until the kernel ends (one global atomic per column per CTA).
-            if (p.stats != nullptr && !(p.dbg & (4 | 32))) {
+            if ((p.stats != nullptr || EPI == 2) && !(p.dbg & (4 | 32))) {
                 int rlim = kBlockM;
                 constexpr bool conv_tile = (AM == LD_CONV);
                 if (conv_tile) rlim = p.th * p.tw;
@@ -559,18 +565,85 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                 }
-                float* scr = s_stats + 2 * p.N;                    // [nparts][2][bn]
+                float* scr = s_stats + (EPI == 2 ? 2 * p.bn : 2 * p.N);   // [nparts][2][bn]
                 float* dst = scr + (part * 2) * p.bn + vec * 8;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { dst[i] = sa[i]; dst[p.bn + i] = sq[i]; }
                 ptx::named_bar_sync(1, 256);
-                for (int jx = tid_e; jx < 2 * p.bn; jx += 256) {
-                    int which, col;
-                    p.fd_bn.divmod(jx, which, col);
-                    if (n0 + col < p.N) {
-                        float tot = 0.f;
-                        for (int pp = 0; pp < nparts; ++pp) tot += scr[(pp * 2 + which) * p.bn + col];
-                        s_stats[which * p.N + n0 + col] += tot;      // single owner per column within the CTA
+                if (EPI != 2) {
+                    for (int jx = tid_e; jx < 2 * p.bn; jx += 256) {
+                        int which, col;
+                        p.fd_bn.divmod(jx, which, col);
+                        if (n0 + col < p.N) {
+                            float tot = 0.f;
+                            for (int pp = 0; pp < nparts; ++pp) tot += scr[(pp * 2 + which) * p.bn + col];
+                            s_stats[which * p.N + n0 + col] += tot;      // single owner per column within the CTA
+                        }
+                    }
+                } else {
+                    // ---- tile-local InstanceNorm (model/attn.py:75-105): this tile holds ALL pixels of one image for bn
+                    // channels, so mean / biased variance over the pixels are complete here.  s_stats[0..bn) = scale
+                    // (gamma * invstd), s_stats[bn..2bn) = shift (beta - mean * scale); mean / invstd saved for backward.
+                    for (int col = tid_e; col < p.bn; col += 256) {
+                        if (n0 + col < p.N) {
+                            float sum = 0.f, sq = 0.f;
+                            for (int pp = 0; pp < nparts; ++pp) { sum += scr[(pp * 2) * p.bn + col]; sq += scr[(pp * 2 + 1) * p.bn + col]; }
+                            const float inv_n = 1.f / static_cast<float>(rlim);
+                            const float mean = sum * inv_n;
+                            const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+                            const float invstd = rsqrtf(var + p.in_eps);
+                            const float sc = __ldg(p.in_gamma + n0 + col) * invstd;
+                            s_stats[col] = sc;
+                            s_stats[p.bn + col] = __ldg(p.in_beta + n0 + col) - mean * sc;
+                            p.in_mean[static_cast<long>(c.batch) * p.N + n0 + col] = mean;
+                            p.in_invstd[static_cast<long>(c.batch) * p.N + n0 + col] = invstd;
+                        }
+                    }
+                    // the raw tile's TMA store must have finished READING the staging buffer before it is normalised in place
+                    if (ew == 0 && ptx::elect_one()) ptx::bulk_wait_read0();
+                    ptx::named_bar_sync(1, 256);
+                    if (scol < p.N) {
+                        float sc8[8], sh8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { sc8[i] = s_stats[vec * 8 + i]; sh8[i] = s_stats[p.bn + vec * 8 + i]; }
+                        for (int r = r0; r < r1; ++r) {
+                            const uint32_t addr = gbase + r * 128 + ((idx ^ (r & 7)) << 4);
+                            uint32_t w4[4];
+                            ptx::ld_shared_v4(addr, w4);
+                            float o[8];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                o[2 * k] = fmaf(__uint_as_float(w4[k] << 16), sc8[2 * k], sh8[2 * k]);
+                                o[2 * k + 1] = fmaf(__uint_as_float(w4[k] & 0xffff0000u), sc8[2 * k + 1], sh8[2 * k + 1]);
+                            }
+                            if (p.in_relu) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] *= p.in_mix;
+                            if (p.in_add != nullptr) {
+                                const long arow = static_cast<long>(c.batch) * p.M + r;
+                                const uint4 aa = __ldg(reinterpret_cast<const uint4*>(p.in_add + arow * p.ldd + scol));
+                                const uint32_t a4[4] = {aa.x, aa.y, aa.z, aa.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    o[2 * k] += __uint_as_float(a4[k] << 16);
+                                    o[2 * k + 1] += __uint_as_float(a4[k] & 0xffff0000u);
+                                }
+                            }
+                            ptx::st_shared_v4(addr, pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();
+                    ptx::named_bar_sync(1, 256);
+                    if (ew == 0 && ptx::elect_one()) {
+                        for (int g = 0; g < ngroups; ++g) {
+                            const int cg = n0 + g * gw;
+                            if (cg >= p.N) break;
+                            ptx::tma_store_3d(&map_e, stg + g * 16384, cg, c.m_t * kBlockM, c.batch);
+                        }
+                        ptx::bulk_commit();
                     }
                 }
             }
@@ -696,6 +769,11 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     const int batch = g->batch > 1 ? g->batch : 1;
     if (batch > 1 && (conv || g->residual || g->d_pre || g->dact_src || g->stats))
         return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: batched form supports the 2-D modes with bias/activation only");
+    const bool inorm = g->d_norm != nullptr;
+    if (inorm && (batch < 2 || g->a_mode != TRIS_OP_K2D || g->b_mode != TRIS_OP_K2D || g->M > kBlockM || g->out_dtype != TRIS_DT_BF16 ||
+                  !g->in_gamma || !g->in_beta || !g->in_mean || !g->in_invstd || g->split_k > 1 || g->atomic || g->b_batch_stride != 0))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: the InstanceNorm epilogue needs the batched K-major form with M <= 128 rows per image, "
+                                          "a shared B, bf16 output and gamma / beta / mean / invstd buffers");
     KParams p{};
     {
         static int dbg = -1;
@@ -783,6 +861,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.staging_bytes = bn * (out_f32 ? 4 : 2) * 128;
     if (p.staging_bytes < 16384) p.staging_bytes = 16384;
     p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 + 16384 : 0;
+    if (inorm) p.stats_bytes = ((2 * bn * 4 + 1023) / 1024) * 1024 + 16384;
     p.nacc = 512 / bn >= 4 ? 4 : 2;   // power of two (ring index = it & (nacc - 1))
     p.acc_stride = bn;
     static uint32_t smem_cap = 0;   // TRIS_GEMM_SMEM_KB: leave shared memory for co-resident streaming kernels (experiment knob)
@@ -790,6 +869,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     const uint32_t fixed = 1024 + sizeof(SmemCtl) + 64 + p.stats_bytes;
     // two staging buffers (store of tile i overlaps the epilogue of tile i+1) when >= 4 pipeline stages still fit
     p.nstg = (smem_cap - fixed - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
+    if (inorm) p.nstg = 1;     // the tile is normalised in place in its staging buffer
     const uint32_t budget = smem_cap - fixed - p.nstg * p.staging_bytes;
     p.stages = budget / stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -812,6 +892,9 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.stats_y = reinterpret_cast<const __nv_bfloat16*>(g->stats_y); p.stats_mu = g->stats_mu;
     p.mask_sc = g->mask_sc; p.mask_sh = g->mask_sh;
     p.tstamp = reinterpret_cast<unsigned long long*>(g->tstamp);
+    p.in_gamma = g->in_gamma; p.in_beta = g->in_beta; p.in_mean = g->in_mean; p.in_invstd = g->in_invstd;
+    p.in_add = reinterpret_cast<const __nv_bfloat16*>(g->in_add);
+    p.in_eps = g->in_eps; p.in_mix = g->in_mix == 0.f ? 1.f : g->in_mix; p.in_relu = g->in_relu;
     p.res_bits = reinterpret_cast<const unsigned char*>(g->res_bits);
     if (g->res_bits && (!g->residual || g->N % 32 || batch > 1 || conv)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: res_bits needs a residual, N %% 32 == 0, plain 2-D mode");
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
@@ -901,15 +984,23 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
         }
     }
     if (!md) return TRIS_ERR_SHAPE;
+    const CUtensorMap* me = md;
+    if (inorm) {
+        uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)g->ldd * 2, (uint64_t)g->d_batch_stride * 2};
+        uint32_t box[3] = {64, (uint32_t)kBlockM, 1};
+        me = tris::tensor_map_bf16(g->d_norm, 3, dims, str, box, 2);
+        if (!me) return TRIS_ERR_SHAPE;
+    }
 
     int am = LD_K2D, bm = LD_K2D;
     if (conv && !wgrad) am = LD_CONV; else if (wgrad) am = LD_CONV_WG; else if (g->a_mode == TRIS_OP_MN2D) am = LD_MN2D;
     if (wgrad) bm = LD_CONV_WG; else if (g->b_mode == TRIS_OP_MN2D) bm = (conv ? LD_MN2D_TAPS : LD_MN2D);
-    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn = nullptr;
-    const int epi = (g->stats_mode == 1 || g->mask_sc != nullptr) ? 1 : 0;
-#define TRIS_PICK(A_, B_) (epi ? static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 1>) : static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 0>))
-    if (am == LD_K2D && bm == LD_K2D) fn = TRIS_PICK(LD_K2D, LD_K2D);
+    const int epi = inorm ? 2 : ((g->stats_mode == 1 || g->mask_sc != nullptr) ? 1 : 0);
+#define TRIS_PICK(A_, B_) (epi == 1 ? static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 1>) : static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 0>))
+    if (am == LD_K2D && bm == LD_K2D) fn = epi == 2 ? static_cast<KernelFn>(tris_umma_gemm_kernel<LD_K2D, LD_K2D, 2>) : TRIS_PICK(LD_K2D, LD_K2D);
     else if (am == LD_K2D && bm == LD_MN2D) fn = TRIS_PICK(LD_K2D, LD_MN2D);
     else if (am == LD_MN2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_MN2D, 0>;
     else if (am == LD_MN2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_K2D, 0>;
@@ -919,7 +1010,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     else return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: unsupported operand mode combination a=%d b=%d", g->a_mode, g->b_mode);
 #undef TRIS_PICK
     if (epi && (am == LD_MN2D || am == LD_CONV_WG)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: BatchNorm-backward epilogue needs a K-major / conv A operand");
-    static bool attr_set[8][8][2] = {};
+    static bool attr_set[8][8][3] = {};
     if (!attr_set[am][bm][epi]) {
         TRIS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[am][bm][epi] = true;
@@ -929,7 +1020,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     if (g->max_ctas > 0 && g->max_ctas < ctas) ctas = g->max_ctas;
     if (total_tiles < ctas) ctas = total_tiles;
     if (g->stats && ctas > g->stats_parts) ctas = g->stats_parts;   // one partial-statistics row per CTA
-    fn<<<ctas, kThreads, smem_bytes, stream>>>(*ma, *mb, *md, p);
+    fn<<<ctas, kThreads, smem_bytes, stream>>>(*ma, *mb, *md, *me, p);
     TRIS_LAUNCH_OK("tris_umma_gemm_kernel");
     if (p.split_ws && !g->defer_reduce) {
         const long total4 = static_cast<long>(g->M) * ws_w / 4;

@@ -165,6 +165,28 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
     return out
 
 
+def linear_in_fwd(x, w, batch, gamma, beta, relu, mix_scale=1.0, mix_add=None, eps=1e-5, block_n=128):
+    """Fused 1x1 conv + InstanceNorm2d(affine) [+ ReLU] [* mix_scale + mix_add] over the P = rows / batch pixels of each image
+    (v_proj / v_output of model/attn.py:75-105): one batched GEMM whose tiles are image-aligned (P <= 128 rows x block_n
+    channels), so the per-(image, channel) statistics are complete inside a tile and the normalisation happens in the epilogue.
+    -> (y raw bf16 [rows, N] (saved for backward), y_norm bf16 [rows, N], mean f32 [batch, N], invstd f32 [batch, N])."""
+    _chk(x, torch.bfloat16, "x"); _chk(w, torch.bfloat16, "w")
+    rows, k = x.shape
+    n = w.shape[0]
+    P = rows // batch
+    assert rows == batch * P and P <= 128 and w.shape[1] == k and batch >= 2 and n % 8 == 0
+    y = torch.empty((rows, n), device=x.device, dtype=torch.bfloat16)
+    yn = torch.empty_like(y)
+    mean = torch.empty((batch, n), device=x.device, dtype=torch.float32)
+    invstd = torch.empty_like(mean)
+    d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(y), d_norm=L.ptr(yn), a_mode=L.OP_K2D, b_mode=L.OP_K2D, M=P, N=n, K=k, lda=k, ldb=k, ldd=n,
+              taps=1, block_n=block_n, split_k=1, out_dtype=L.DT_BF16, batch=batch, a_batch_stride=P * k, b_batch_stride=0,
+              d_batch_stride=P * n, in_gamma=L.ptr(gamma), in_beta=L.ptr(beta), in_mean=L.ptr(mean), in_invstd=L.ptr(invstd),
+              in_add=L.ptr(mix_add), in_eps=eps, in_mix=mix_scale, in_relu=int(relu))
+    L.gemm_raw(d)
+    return y, yn, mean, invstd
+
+
 def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block_n=None, dact_src=None,
                  act=L.ACT_NONE, bias=None, bwd_stats=None, res_bits=None):
     """dx[M,K] = dy[M,N] @ w[N,K]   (w read MN-major: no transposed weight copy)."""

@@ -26,6 +26,9 @@ from . import ops
 
 bf16, f32 = torch.bfloat16, torch.float32
 K2D, MN2D = L.OP_K2D, L.OP_MN2D
+import os
+# 1x1 conv + InstanceNorm [+ ReLU / 0.1-mix] as ONE batched GEMM with a tile-local normalisation epilogue (gemm.linear_in_fwd)
+FUSE_IN = os.environ.get("TRIS_FUSE_IN", "1") != "0"
 MIX = 0.1   # hard-coded in the reference (model_stage1.py:73-74); args.attn_multi only gates the fusion on/off
 
 
@@ -75,8 +78,12 @@ class Stage1Head:
             # left out so that the bf16 rounding of Yv / Ov is relative to the pixel-varying part only
             # and the operand is centred over the pixels of each image in fp32 first (ops.center_pixels): exact, see misc.cu
             nvc = ops.center_pixels(nv32, B)
-            Yv = G.linear_fwd(nvc, W["Wqkv"])                                                   # [BP, 3C]
-            A3, mu3, is3 = ops.instnorm_fwd(Yv, Pf["gqkv"], Pf["beqkv"], B, relu=True)
+            fused_in = FUSE_IN and B >= 2 and Pn <= 128
+            if fused_in:      # Q|K|V projection + InstanceNorm + ReLU in one kernel (image-aligned tiles)
+                Yv, A3, mu3, is3 = G.linear_in_fwd(nvc, W["Wqkv"], B, Pf["gqkv"], Pf["beqkv"], relu=True)
+            else:
+                Yv = G.linear_fwd(nvc, W["Wqkv"])                                               # [BP, 3C]
+                A3, mu3, is3 = ops.instnorm_fwd(Yv, Pf["gqkv"], Pf["beqkv"], B, relu=True)
             At3 = G.linear_fwd(nl, W["Wt"], Pf["bt"], act=L.ACT_RELU)                           # [T, 3C]
             qv, kv, vv = A3[:, :C], A3[:, C:2 * C], A3[:, 2 * C:]
             qt, kt, vt = At3[:, :C], At3[:, C:2 * C], At3[:, 2 * C:]
@@ -90,8 +97,11 @@ class Stage1Head:
             nlp = torch.empty((B * T, C), device=dev, dtype=bf16)
             G.gemm_ex(PTt, vv, nlp, T, C, Pn, a_mode=MN2D, b_mode=MN2D, lda=Tp, ldb=3 * C, batch=B, a_bs=Pn * Tp,
                       b_bs=Pn * 3 * C, d_bs=T * C)                                              # PT_b Vv_b
-            Ov = G.linear_fwd(nvp, W["Wo"])
-            vp, muo, iso = ops.instnorm_fwd(Ov, Pf["go"], Pf["beo"], B, relu=False, mix_scale=MIX, mix_add=nv)
+            if fused_in:      # v_output + InstanceNorm + 0.1-mix + residual in one kernel
+                Ov, vp, muo, iso = G.linear_in_fwd(nvp, W["Wo"], B, Pf["go"], Pf["beo"], relu=False, mix_scale=MIX, mix_add=nv)
+            else:
+                Ov = G.linear_fwd(nvp, W["Wo"])
+                vp, muo, iso = ops.instnorm_fwd(Ov, Pf["go"], Pf["beo"], B, relu=False, mix_scale=MIX, mix_add=nv)
             Ol = G.linear_fwd(nlp, W["Wto"], Pf["bto"])
             lp = ops.bcast_mix(nl, Ol, MIX)                                                     # [B*T, C]
             lp_bs = T * C
