@@ -189,6 +189,13 @@ int tris_mask_resize_fwd(const float* sig, const float* img, void* patches, floa
 /* gradient of the above w.r.t. the sigmoid map. */
 int tris_mask_resize_bwd(const void* dpatches, const float* img, float* dcam, float* dsig, int B, int S, int O, int
     ps, tris_stream_t stream);
+/* PRMS map selection (validate.py:120-127, 304-332): cosine scores of the S masked-image features f [S, D] against the S
+ * sentence features g [S, D] (bf16), summed over the sentences; *best = first arg-max, scores [S] optional. */
+int tris_prms_select(const void* f, const void* g, float* scores, int* best, int S, int D, tris_stream_t stream);
+/* validate.py:183-191 on the device: out = cam / (max + 1e-5), pred = out > 1e-9, stats = {|pred & target|, |pred | target|,
+ * hit (target at the first arg-max), max}.  cams f32 [S, HW] with *sel choosing the map (NULL: map 0); target int64 [HW]. */
+int tris_cam_metrics(const float* cams, const int* sel, const long long* target, float* out, float* stats, int HW,
+    tris_stream_t stream);
 /* F.interpolate(mode="bilinear", align_corners=True) of fp32 [nc, H, W] maps to the original image size (validate.py:180, demo.py:94). */
 int tris_resize_bilinear_ac(const float* src, float* dst, long nc, int H, int W, int OH, int OW, tris_stream_t stream);
 /* fg loss (clip_forward + MaxLoss, train_stage1.py:263-284,340), negative loss (:342-353), multilabel soft margin (:354), weighted sum (:364). */

@@ -171,3 +171,41 @@ def test_reference_validate_prms_on_tris_b200_bf16(ref, tmp_path):
         agree += int(np.abs(a - b).max() <= 8e-2)
     print("PRMS bf16: CAMs agreeing with the reference", agree, "of 6")
     assert agree >= 4     # near-tied candidates at random init may flip under bf16 (see the fp32 test above)
+
+
+def test_repo_prms_driver_against_reference_driver(ref, tmp_path):
+    """This repo's validate.py --prms --save_cam (RN50 once per ref, S instead of S^2 scorer passes, device-side selection and
+    metrics, asynchronous .npy writer) against the reference's validate_same_sentence on the same synthetic refs: same file
+    names, same names JSON, maps that agree wherever the candidates are not a numerical tie, mIoU within a point."""
+    import validate as MyV
+    RS, ns, args = ref
+    n, S = 8, 2
+    loader = RS.make_val_loader(n, sentences=S)
+    model, aux = RS.build_models(ns, args, "cuda", aux_half=False)
+    d_ref = str(tmp_path / "r")
+    os.makedirs(d_ref)
+    m_ref = _run_validate(ns, args, model, loader, aux, True, d_ref)
+    del model, aux
+    model, aux = _ours(args)
+    d_our = str(tmp_path / "o")
+    args.cam_save_dir, args.name_save_dir, args.save_cam = os.path.join(d_our, "cam"), os.path.join(d_our, "names"), True
+    args.val_refs, args.no_graph, args.precision = n, False, "bf16"
+    miou = MyV.validate_same_sentence(args, MyV.synthetic_refs(args, n, sentences=S), model, aux)
+    fr, fo = sorted(os.listdir(os.path.join(d_ref, "cam"))), sorted(os.listdir(os.path.join(d_our, "cam")))
+    assert fr == fo and len(fr) == n
+    nj = f"{args.dataset}_train_names.json"
+    assert sorted(json.load(open(os.path.join(d_ref, "names", nj)))) == sorted(json.load(open(os.path.join(d_our, "names", nj))))
+    agree = sum(int(np.abs(np.load(os.path.join(d_ref, "cam", f)) - np.load(os.path.join(d_our, "cam", f))).max() <= 8e-2) for f in fr)
+    print("repo PRMS driver vs reference driver: maps agreeing", agree, "of", n, "| mIoU", 100 * miou, "vs", float(m_ref[1]))
+    assert agree >= n - 2
+    assert abs(100 * miou - float(m_ref[1])) <= 2.0
+    # the plain driver (every sentence of every ref) against the reference's validate() on the same refs
+    args.save_cam = False
+    model_r, _ = RS.build_models(ns, args, "cuda", aux_half=False)
+    d2 = str(tmp_path / "r2")
+    os.makedirs(d2)
+    m_ref2 = _run_validate(ns, args, model_r, loader, None, False, d2)
+    args.save_cam, args.cam_save_dir = False, None
+    miou2, hit2 = MyV.validate(args, MyV.synthetic_refs(args, n, sentences=S), model)
+    print("repo validate driver vs reference validate: mIoU", 100 * miou2, "vs", float(m_ref2[1]), "| hit", 100 * hit2, "vs", float(m_ref2[2]))
+    assert abs(100 * miou2 - float(m_ref2[1])) <= 2.0 and abs(100 * hit2 - float(m_ref2[2])) <= 100.0 / n + 1e-6

@@ -622,6 +622,94 @@ int grid_for(long n, int threads) {
     return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+
+// ------------------------------------------------------------------------------------------------ PRMS (validate.py:304-332)
+// get_scores (validate.py:120-127) for the S candidate maps of a ref against its S sentences, summed over the sentences, and
+// the arg-max (first maximum wins, like the reference's `score > max_info['score']`).  f [S, D] image features of fg_j,
+// g [S, D] text features; one CTA, warp w handles candidates w, w + nwarps, ...
+__global__ void __launch_bounds__(256) prms_select_kernel(const __nv_bfloat16* __restrict__ f, const __nv_bfloat16* __restrict__ g,
+                                                          float* __restrict__ scores, int* __restrict__ best, int S, int D) {
+    __shared__ float s_ng[32], s_sc[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < S; j += nw) {
+        float q = 0.f;
+        for (int d = lane; d < D; d += 32) { const float x = __bfloat162float(g[j * D + d]); q = fmaf(x, x, q); }
+        q = warp_sum(q);
+        if (lane == 0) s_ng[j] = rsqrtf(q);
+    }
+    __syncthreads();
+    for (int i = warp; i < S; i += nw) {
+        float q = 0.f;
+        for (int d = lane; d < D; d += 32) { const float x = __bfloat162float(f[i * D + d]); q = fmaf(x, x, q); }
+        const float nf = rsqrtf(warp_sum(q));
+        float tot = 0.f;
+        for (int j = 0; j < S; ++j) {
+            float dot = 0.f;
+            for (int d = lane; d < D; d += 32) dot = fmaf(__bfloat162float(f[i * D + d]), __bfloat162float(g[j * D + d]), dot);
+            tot += warp_sum(dot) * nf * s_ng[j];
+        }
+        if (lane == 0) s_sc[i] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int i = 0; i < S; ++i) {
+            if (scores != nullptr) scores[i] = s_sc[i];
+            if (s_sc[i] > s_sc[b]) b = i;
+        }
+        *best = b;
+    }
+}
+
+// validate.py:183-191 for one map: cam /= max + 1e-5 ; pred = cam > 1e-9 ; I = |pred & target|, U = |pred | target| ; pointing
+// game: does the (first) arg-max fall on the target?  cams [S, H*W] with *sel choosing the map (PRMS) or sel == nullptr -> map 0.
+// out [H*W] normalised map ; stats[4] = I, U, hit, max.  One CTA of 1024 threads (the map is L2-resident).
+__global__ void __launch_bounds__(1024) cam_metrics_kernel(const float* __restrict__ cams, const int* __restrict__ sel,
+                                                           const long long* __restrict__ target, float* __restrict__ out,
+                                                           float* __restrict__ stats, int HW) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    __shared__ float s_a[32], s_b[32];
+    const float* cam = cams + static_cast<long>(sel != nullptr ? *sel : 0) * HW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mv = -3.4e38f;
+    int mi = 0x7fffffff;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float v = cam[i];
+        if (v > mv) { mv = v; mi = i; }         // strided scan: indices increase, so the first maximum of this thread is kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) { s_v[warp] = mv; s_i[warp] = mi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w)
+            if (s_v[w] > s_v[0] || (s_v[w] == s_v[0] && s_i[w] < s_i[0])) { s_v[0] = s_v[w]; s_i[0] = s_i[w]; }
+    }
+    __syncthreads();
+    const float inv = 1.f / (s_v[0] + 1e-5f);
+    float ii = 0.f, uu = 0.f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float v = cam[i] * inv;
+        out[i] = v;
+        const bool p = v > 1e-9f, t = target[i] != 0;
+        ii += (p && t) ? 1.f : 0.f;
+        uu += (p || t) ? 1.f : 0.f;
+    }
+    ii = warp_sum(ii); uu = warp_sum(uu);
+    if (lane == 0) { s_a[warp] = ii; s_b[warp] = uu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 32; ++w) { a += s_a[w]; b += s_b[w]; }
+        stats[0] = a; stats[1] = b; stats[2] = target[s_i[0]] != 0 ? 1.f : 0.f; stats[3] = s_v[0];
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -724,6 +812,19 @@ int tris_mask_resize_bwd(const void* dpatches, const float* img, float* dcam, fl
     TRIS_LAUNCH_OK("mask_resize_dcam");
     mask_resize_dsig_kernel<<<grid_for(static_cast<long>(B) * S * S, 256), 256, 0, (cudaStream_t)stream>>>(dcam, dsig, B, S, O);
     TRIS_LAUNCH_OK("mask_resize_dsig");
+    return TRIS_OK;
+}
+
+int tris_prms_select(const void* f, const void* g, float* scores, int* best, int S, int D, tris_stream_t stream) {
+    if (S < 1 || S > 32) return tris::fail(TRIS_ERR_SHAPE, "tris_prms_select: 1 <= S <= 32 sentences (got %d)", S);
+    prms_select_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)f, (const __nv_bfloat16*)g, scores, best, S, D);
+    TRIS_LAUNCH_OK("prms_select_kernel");
+    return TRIS_OK;
+}
+
+int tris_cam_metrics(const float* cams, const int* sel, const long long* target, float* out, float* stats, int HW, tris_stream_t stream) {
+    cam_metrics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cams, sel, target, out, stats, HW);
+    TRIS_LAUNCH_OK("cam_metrics_kernel");
     return TRIS_OK;
 }
 

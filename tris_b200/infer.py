@@ -54,8 +54,20 @@ class Stage1Inference:
             self._resp = GraphRunner(lambda c, i: self.model.respond(c, i, img_size), c4, ids)
         return self._resp(c4, ids)
 
+    def prms_features(self, cams, img, ids):
+        """(f [S, 512], g [S, 512]) bf16: features of fg_j = cam_j * img (224 x 224) and of the S sentences of the ref
+        (validate.py:304-332); scored on the device by ops.prms_select."""
+        return self._prms(cams, img, ids)
+
     def prms_scores(self, cams, img, ids):
-        """[S, S] cosine scores of fg_j = cam_j * img (224 x 224) against every sentence of the ref (validate.py:304-332)."""
+        """[S, S] cosine scores of fg_j against every sentence of the ref, as a host-visible matrix (diagnostics / tests)."""
+        f, g = self._prms(cams, img, ids)
+        f, g = f.float(), g.float()
+        f = f / f.norm(dim=-1, keepdim=True)
+        g = g / g.norm(dim=-1, keepdim=True)
+        return f @ g.t()
+
+    def _prms(self, cams, img, ids):
         from . import ops
         eng = self.aux._engine()
         S = ids.shape[0]
@@ -70,10 +82,7 @@ class Stage1Inference:
                 eng.ensure_fresh()
                 self._score[S] = GraphRunner(run, cams, img, ids)
             f, g = self._score[S](cams, img, ids)
-        f, g = f.float(), g.float()
-        f = f / f.norm(dim=-1, keepdim=True)
-        g = g / g.norm(dim=-1, keepdim=True)
-        return f @ g.t()
+        return f, g
 
 
 class AsyncCamWriter:
@@ -88,13 +97,21 @@ class AsyncCamWriter:
         self.out_dir, self.pool, self.pending = out_dir, ThreadPoolExecutor(max_workers=workers), []
         self.stream = torch.cuda.Stream()
         self.names = []
+        self._free = {}          # shape -> pinned host buffers whose file has been written (cudaHostAlloc per map is slow)
+        import threading
+        self._lock = threading.Lock()
 
     def submit(self, name, cam):
         import os
         import numpy as np
         self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
+        key = (tuple(cam.shape), cam.dtype)
+        with self._lock:
+            pool = self._free.setdefault(key, [])
+            host = pool.pop() if pool else None
+        if host is None:
             host = torch.empty(cam.shape, dtype=cam.dtype, pin_memory=True)
+        with torch.cuda.stream(self.stream):
             host.copy_(cam, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -104,6 +121,8 @@ class AsyncCamWriter:
         def work():
             ev.synchronize()
             np.save(path, host.numpy())
+            with self._lock:
+                self._free[key].append(host)
         self.pending.append(self.pool.submit(work))
         self.names.append(name)
 

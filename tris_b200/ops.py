@@ -409,3 +409,23 @@ def resize_bilinear_ac(x, oh, ow):
     out = torch.empty((n, c, oh, ow), device=x.device, dtype=f32)
     L.call("tris_resize_bilinear_ac", _vp(x.contiguous()), _vp(out), C.c_long(n * c), h, w, oh, ow)
     return out
+
+
+def prms_select(f, g):
+    """f, g bf16 [S, D] -> (best int32 [1] on the device, scores f32 [S]): PRMS choice without a host round trip."""
+    S, D = f.shape
+    scores = torch.empty((S,), device=f.device, dtype=f32)
+    best = torch.empty((1,), device=f.device, dtype=torch.int32)
+    L.call("tris_prms_select", _vp(f.contiguous()), _vp(g.contiguous()), _vp(scores), _vp(best), S, D)
+    return best, scores
+
+
+def cam_metrics(cams, target, sel=None, stats=None):
+    """cams f32 [S, H, W] (or [H, W]), target int64 [H, W] -> (normalised map f32 [H, W], stats f32 [4] = I, U, hit, max)."""
+    hw = target.numel()
+    cams = cams.reshape(-1, hw).contiguous()
+    out = torch.empty(target.shape, device=cams.device, dtype=f32)
+    if stats is None:
+        stats = torch.empty((4,), device=cams.device, dtype=f32)
+    L.call("tris_cam_metrics", _vp(cams), _vp(sel), _vp(target.contiguous()), _vp(out), _vp(stats), hw)
+    return out, stats

@@ -45,62 +45,73 @@ def _to_original(cam, size):
     return ops.resize_bilinear_ac(cam.contiguous(), size[0], size[1])
 
 
-def _iou_hit(cam, target):
-    cam = cam / (cam.max() + 1e-5)
-    pred = cam > 1e-9
-    tgt = target.bool()
-    inter, union = (pred & tgt).sum().item(), (pred | tgt).sum().item()
-    peak = int(cam.reshape(-1).argmax())
-    hit = bool(tgt.reshape(-1)[peak])
-    return inter / max(union, 1), hit, cam
+def _finish(stats, n):
+    """One device->host read for the whole run: stats f32 [n, 4] = I, U, hit, max per evaluated map."""
+    h = stats[:n].cpu().double().numpy()
+    iou = h[:, 0] / np.maximum(h[:, 1], 1.0)
+    return (float(iou.mean()) if n else 0.0), (float(h[:, 2].mean()) if n else 0.0)
 
 
 @torch.no_grad()
 def validate(args, refs, model, local_rank=0):
-    from tris_b200.infer import Stage1Inference
+    """validate.py:131-249 of the reference, per ref and sentence: map -> bilinear(align_corners=True) to the original
+    size -> /max -> threshold 1e-9 -> IoU / pointing-game hit.  Everything stays on the device (tris_cam_metrics); the
+    host reads the per-map statistics once at the end instead of three times per sentence."""
+    from tris_b200 import ops
+    from tris_b200.infer import AsyncCamWriter, Stage1Inference
     inf = Stage1Inference(model, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
-    ious, hits = [], []
+    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
+    stats = torch.zeros((max(1, args.val_refs) * 8, 4), device="cuda")
+    n = 0
     for idx, img, word_ids, target in refs:
-        img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
+        img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
         c4 = inf.features(img)                                  # once per ref
         for j in range(word_ids.shape[-1]):
             out = inf.respond(c4, word_ids[:, :, j].contiguous(), tuple(img.shape[2:]))
-            cam = _to_original(out, target.shape[-2:])[0, 0]
-            iou, hit, cam = _iou_hit(cam, target[0])
-            ious.append(iou)
-            hits.append(hit)
-            if args.save_cam and args.cam_save_dir:
-                os.makedirs(args.cam_save_dir, exist_ok=True)
-                np.save(os.path.join(args.cam_save_dir, f"{idx}_{j}.npy"), cam.cpu().numpy())
-    return float(np.mean(ious)) if ious else 0.0, float(np.mean(hits)) if hits else 0.0
+            cam = _to_original(out, target.shape[-2:])
+            if n >= stats.shape[0]:
+                stats = torch.cat([stats, torch.zeros_like(stats)])
+            cam_n, _ = ops.cam_metrics(cam, target[0], stats=stats[n])
+            n += 1
+            if writer is not None:
+                writer.submit(f"{idx}_{j}", cam_n)
+    if writer is not None:
+        writer.close()
+    return _finish(stats, n)
 
 
 @torch.no_grad()
 def validate_same_sentence(args, refs, model, aux, local_rank=0):
-    """PRMS map selection (validate.py:253-387) with per-ref de-duplicated encoders."""
-    from tris_b200.infer import Stage1Inference
+    """PRMS map selection (validate.py:253-387) with per-ref de-duplicated encoders: the RN50 tower runs once per ref, each
+    candidate map and each sentence is encoded once (S ViT + S text passes instead of S^2), and the choice of the map
+    (tris_prms_select), the resize and the metrics (tris_cam_metrics) never leave the device."""
+    from tris_b200 import ops
+    from tris_b200.infer import AsyncCamWriter, Stage1Inference
     inf = Stage1Inference(model, aux, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
-    from tris_b200.infer import AsyncCamWriter
     writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
-    ious, names = [], []
+    stats = torch.zeros((max(1, args.val_refs), 4), device="cuda")
+    names, n = [], 0
     for idx, img, word_ids, target in refs:
-        img, word_ids, target = img.cuda(), word_ids.cuda(), target.cuda()
+        img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
         S = word_ids.shape[-1]
         ids = word_ids[0].t().contiguous()                                     # [S, L]
         c4 = inf.features(img)
         cams = torch.cat([inf.respond(c4, ids[j:j + 1], tuple(img.shape[2:])).clone() for j in range(S)])   # [S,1,H,W]
-        best = int(inf.prms_scores(cams, img, ids).sum(dim=1).argmax())         # get_scores summed over the ref's sentences
-        cam = _to_original(cams[best:best + 1], target.shape[-2:])[0, 0]
-        iou, _, cam = _iou_hit(cam, target[0])
-        ious.append(iou)
+        f, g = inf.prms_features(cams, img, ids)
+        best, _ = ops.prms_select(f, g)                                         # device-side arg-max of the summed get_scores
+        big = _to_original(cams, target.shape[-2:])                             # [S,1,oH,oW]
+        if n >= stats.shape[0]:
+            stats = torch.cat([stats, torch.zeros_like(stats)])
+        cam_n, _ = ops.cam_metrics(big, target[0], sel=best, stats=stats[n])
+        n += 1
         if writer is not None:
-            writer.submit(f"{idx}_{idx}", cam)                                   # {idx}_{img_id}.npy, written in the background
+            writer.submit(f"{idx}_{idx}", cam_n)                                 # {idx}_{img_id}.npy, written in the background
     if writer is not None:
         names = writer.close()
     if args.save_cam and args.name_save_dir:
         os.makedirs(args.name_save_dir, exist_ok=True)
         json.dump(names, open(os.path.join(args.name_save_dir, f"{args.dataset}_train_names.json"), "w"))
-    return float(np.mean(ious)) if ious else 0.0
+    return _finish(stats, n)[0]
 
 
 def main(args):
