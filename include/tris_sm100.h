@@ -104,6 +104,9 @@ typedef struct tris_gemm_desc {
     const void* in_add;   /* optional bf16 [batch*M, ldd] */
     float in_eps, in_mix; /* in_mix 0 is read as 1 */
     int32_t in_relu;
+    int32_t conv_halo;    /* 1 = 3x3 conv forward / dgrad with halo re-use: the (16+2) x (8+2) pixel box of a 16 x 8 tile is loaded
+                             once per 64-channel block and the nine taps are nine start addresses into it (instead of nine
+                             shifted box loads); needs tile_h = 16, tile_w = 8 */
     const void* res_bits; /* optional uint8 [M, N/8] (N % 32 == 0): the residual is added only where its bit is set -- the residual
                              join of a bottleneck in backward: dx = dy1 W1 + dout * [out > 0] without materialising the masked
                              gradient (bits from tris_bn_apply_fwd) */

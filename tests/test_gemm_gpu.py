@@ -74,8 +74,10 @@ def test_linear_wgrad(G, m, n, k):
     assert rel(out1, dy.float().t() @ x.float()) < 2e-3
 
 
+# (the first, and the last four, tile into 16 x 8 patches: they run the halo-re-use form of the kernel)
 CONV_CASES = [(2, 80, 80, 64, 64), (3, 40, 40, 128, 128), (2, 20, 20, 256, 256), (3, 10, 10, 512, 512),
-              (1, 20, 20, 512, 512), (2, 12, 9, 64, 128)]
+              (1, 20, 20, 512, 512), (2, 12, 9, 64, 128), (2, 32, 16, 64, 64), (3, 16, 8, 128, 64), (2, 48, 24, 64, 128),
+              (24, 160, 160, 64, 128)]
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", CONV_CASES)

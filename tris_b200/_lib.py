@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("defer_reduce", C.c_int32), ("split_used", C.c_int32),
         ("d_norm", C.c_void_p), ("in_gamma", C.c_void_p), ("in_beta", C.c_void_p), ("in_mean", C.c_void_p), ("in_invstd", C.c_void_p),
         ("in_add", C.c_void_p), ("in_eps", C.c_float), ("in_mix", C.c_float), ("in_relu", C.c_int32),
+        ("conv_halo", C.c_int32),
         ("res_bits", C.c_void_p), ("tstamp", C.c_void_p),
     ]
 

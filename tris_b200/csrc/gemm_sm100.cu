@@ -20,7 +20,8 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kThreads = 352;   // warp 0 TMA(A), warp 1 MMA, warps 2-9 epilogue, warp 10 TMA(B)
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 9;    // barrier slots; the streaming rings use at most kRingStages, the resident-weight form all nine
+constexpr int kRingStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kMaxAcc = 4;       // TMEM accumulator ring: min(4, 512 / BN) buffers of BN fp32 columns
 
@@ -64,6 +65,12 @@ struct KParams {
     const float* stats_mu;           // mode 1: per-column mean [N]
     const float* mask_sc;            // optional [N]: multiply the output by ((stats_y * mask_sc + mask_sh) > 0)  (ReLU mask
     const float* mask_sh;            //   of relu(bn(y)) recomputed from y)
+    // LD_CONV_HALO: the (th+2) x (tw+2) pixel box of a tile is loaded ONCE per 64-channel block; the nine taps are nine start
+    // addresses into it (K-major SWIZZLE_128B operands work with row-shifted starts and a non-1024 group stride: the swizzle is
+    // a function of the absolute smem address -- tools/micro/umma_shift.cu)
+    uint32_t a_stages, a_stage_bytes, halo_pitch;   // ring depth, bytes per halo tile (1024-aligned), tw + 2
+    uint32_t ring_bytes;             // bytes of all operand rings (staging starts there)
+    int b_stationary;                // halo form, 64 input channels, one N tile: the nine weight tiles are loaded ONCE per CTA
     int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
     const unsigned char* res_bits;   // optional [M, N/8]: residual added only where its bit is set
     // EPI 2 (tile-local InstanceNorm: batched mode, one tile = the M <= 128 pixels of one image x bn channels)
@@ -84,6 +91,8 @@ struct SmemCtl {
     uint64_t empty[kMaxStages];
     uint64_t acc_full[kMaxAcc];
     uint64_t acc_empty[kMaxAcc];
+    uint64_t afull[4];    // LD_CONV_HALO: ring of halo tiles (A), decoupled from the per-tap weight ring (full / empty)
+    uint64_t aempty[4];
     uint32_t tmem_base;
 };
 
@@ -131,7 +140,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 // Loader variants (compile-time, so the single-thread producer / issuer loops carry no mode branches or divisions)
-enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4 };
+enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4, LD_CONV_HALO = 5 };
 
 // EPI = 1 adds the BatchNorm-backward epilogue (recomputed ReLU mask from y, sums (g, g (y - mu))): compiled separately so
 // that the common kernels do not carry its code.
@@ -148,7 +157,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.stages * stage_bytes + p.nstg * p.staging_bytes + p.stats_bytes);
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.ring_bytes + p.nstg * p.staging_bytes + p.stats_bytes);
     const uint32_t smem_base = ptx::smem_u32(smem);
 
     const int warp = threadIdx.x >> 5;
@@ -165,8 +174,12 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         ptx::prefetch_tmap(&map_b);
         ptx::prefetch_tmap(&map_d);
         for (uint32_t s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&ctl->full[s]), 2);
+            ptx::mbar_init(ptx::smem_u32(&ctl->full[s]), AM == LD_CONV_HALO ? 1 : 2);   // halo form: only the B producer arms it
             ptx::mbar_init(ptx::smem_u32(&ctl->empty[s]), 1);
+        }
+        for (int s = 0; s < 4; ++s) {
+            ptx::mbar_init(ptx::smem_u32(&ctl->afull[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&ctl->aempty[s]), 1);
         }
         for (int b = 0; b < kMaxAcc; ++b) {
             ptx::mbar_init(ptx::smem_u32(&ctl->acc_full[b]), 1);
@@ -189,7 +202,57 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 0 || warp == 10) {
         // ------------------------------------------------------------------ TMA producers: warp 0 feeds A, warp 10 feeds B
         // (two single-thread issue loops in parallel; each arms the stage's full barrier with its own byte count)
-        if (ptx::elect_one()) {
+        if (AM == LD_CONV_HALO) {
+            if (ptx::elect_one()) {
+                const uint32_t b_ring = smem_base + p.a_stages * p.a_stage_bytes;
+                if (warp == 0) {      // A: one halo box per (tile, 64-channel block)
+                    uint32_t as = 0, aph = 0;
+                    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                        const TileCoord c = decode_tile(p, t);
+                        for (int cb = 0; cb < p.cblocks; ++cb) {
+                            ptx::mbar_wait(ptx::smem_u32(&ctl->aempty[as]), aph ^ 1);
+                            const uint32_t bar = ptx::smem_u32(&ctl->afull[as]);
+                            ptx::mbar_expect_tx(bar, p.a_tx);
+                            ptx::tma_load_4d(smem_base + as * p.a_stage_bytes, &map_a, bar, cb * 64, c.w0 - 1, c.h0 - 1, c.n_i);
+                            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                        }
+                    }
+                } else if (p.b_stationary) {   // B: the nine weight tiles of the layer, once (stage = tap, never released)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t bar = ptx::smem_u32(&ctl->full[tap]);
+                        const uint32_t sb = b_ring + tap * p.b_bytes;
+                        ptx::mbar_expect_tx(bar, p.b_tx);
+                        if (BM == LD_K2D) {
+                            ptx::tma_load_2d(sb, &map_b, bar, tap * 64, 0);
+                        } else {
+                            for (int j = 0; j < p.bn / 64; ++j)
+                                ptx::tma_load_2d(sb + j * p.b_atom, &map_b, bar, tap * p.b_tap_stride + 64 * j, 0);
+                        }
+                    }
+                } else {              // B: one weight tile per (tile, channel block, tap)
+                    uint32_t stage = 0, phase = 0;
+                    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                        const TileCoord c = decode_tile(p, t);
+                        const int n0 = c.n_t * p.bn;
+                        for (int cb = 0; cb < p.cblocks; ++cb)
+                            for (int tap = 0; tap < 9; ++tap) {
+                                ptx::mbar_wait(ptx::smem_u32(&ctl->empty[stage]), phase ^ 1);
+                                const uint32_t bar = ptx::smem_u32(&ctl->full[stage]);
+                                const uint32_t sb = b_ring + stage * p.b_bytes;
+                                ptx::mbar_expect_tx(bar, p.b_tx);
+                                if (BM == LD_K2D) {
+                                    ptx::tma_load_2d(sb, &map_b, bar, (tap * p.cblocks + cb) * 64, n0);
+                                } else {
+                                    const int inner = tap * p.b_tap_stride + n0;
+                                    for (int j = 0; j < p.bn / 64; ++j)
+                                        ptx::tma_load_2d(sb + j * p.b_atom, &map_b, bar, inner + 64 * j, cb * 64);
+                                }
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
+                    }
+                }
+            }
+        } else if (ptx::elect_one()) {
             const bool is_a = warp == 0;
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -277,7 +340,66 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ UMMA issuer (single elected thread)
-        if (ptx::elect_one()) {
+        if (AM == LD_CONV_HALO) {
+            if (ptx::elect_one()) {
+                uint32_t stage = 0, phase = 0, as = 0, aph = 0, acc_phase = 0;
+                int it = 0;
+                constexpr bool b_mn = (BM != LD_K2D);
+                constexpr uint32_t b_kstep = (b_mn ? 2048u : 32u) >> 4;
+                const uint64_t da0 = ptx::umma_smem_desc_sw128(0, 0u, p.halo_pitch * 128);   // 8-row groups = patch rows, pitch tw + 2
+                const uint64_t db0 = ptx::umma_smem_desc_sw128(0, b_mn ? p.b_atom : 0u, 1024);
+                const uint32_t b_ring = smem_base + p.a_stages * p.a_stage_bytes;
+                const int sgn = p.flip ? -1 : 1;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                    const int buf = it & (p.nacc - 1);
+                    ptx::mbar_wait(ptx::smem_u32(&ctl->acc_empty[buf]), ((acc_phase >> buf) & 1) ^ 1);
+                    acc_phase ^= 1u << buf;
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * p.acc_stride;
+                    uint32_t accum = 0;
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        ptx::mbar_wait(ptx::smem_u32(&ctl->afull[as]), aph);
+                        const uint32_t a_tile = smem_base + as * p.a_stage_bytes;
+                        if (p.b_stationary) {
+                            // resident weights (stage = tap): their barriers completed phase 0 once and for all
+                            if (it == 0) {
+                                for (int tap = 0; tap < 9; ++tap) ptx::mbar_wait(ptx::smem_u32(&ctl->full[tap]), 0);
+                            }
+                            ptx::tc_fence_after();
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int dr = tap / 3 - 1, ds = tap % 3 - 1;
+                                const uint32_t sa = (a_tile + static_cast<uint32_t>((1 + sgn * dr) * static_cast<int>(p.halo_pitch) + 1 + sgn * ds) * 128u) >> 4;
+                                const uint32_t sb = (b_ring + tap * p.b_bytes) >> 4;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    ptx::umma_f16(tmem_d, da0 | static_cast<uint64_t>(sa + k * 2), db0 | static_cast<uint64_t>(sb + k * b_kstep), p.idesc, accum);
+                                    accum = 1;
+                                }
+                            }
+                        } else {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int dr = tap / 3 - 1, ds = tap % 3 - 1;
+                                const uint32_t sa = (a_tile + static_cast<uint32_t>((1 + sgn * dr) * static_cast<int>(p.halo_pitch) + 1 + sgn * ds) * 128u) >> 4;
+                                ptx::mbar_wait(ptx::smem_u32(&ctl->full[stage]), phase);
+                                ptx::tc_fence_after();
+                                const uint32_t sb = (b_ring + stage * p.b_bytes) >> 4;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    ptx::umma_f16(tmem_d, da0 | static_cast<uint64_t>(sa + k * 2), db0 | static_cast<uint64_t>(sb + k * b_kstep), p.idesc, accum);
+                                    accum = 1;
+                                }
+                                ptx::umma_commit(ptx::smem_u32(&ctl->empty[stage]));
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                        ptx::umma_commit(ptx::smem_u32(&ctl->aempty[as]));
+                        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&ctl->acc_full[buf]));
+                }
+            }
+        } else if (ptx::elect_one()) {
             uint32_t stage = 0, phase = 0;
             uint32_t acc_phase = 0;   // bit b = phase of accumulator buffer b
             int it = 0;
@@ -327,8 +449,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int half = ew >> 2;
         const int tid_e = threadIdx.x - 64;
         const int row = q * 32 + lane;
-        const uint32_t stg0 = smem_base + p.stages * stage_bytes;
-        float* s_stats = reinterpret_cast<float*>(smem + p.stages * stage_bytes + p.nstg * p.staging_bytes);
+        const uint32_t stg0 = smem_base + p.ring_bytes;
+        float* s_stats = reinterpret_cast<float*>(smem + p.ring_bytes + p.nstg * p.staging_bytes);
         const int esz = p.out_f32 ? 4 : 2;
         const int gw = 128 / esz;                      // columns per 128-byte staging group
         const int ngroups = (p.bn * esz) / 128;
@@ -382,7 +504,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     // g = acc * [relu(bn(y)) > 0], the mask recomputed from y (one 64-byte row segment per thread)
                     long yrow = grow;
                     bool yok = rvalid;
-                    if (AM == LD_CONV) {
+                    if (AM == LD_CONV || AM == LD_CONV_HALO) {
                         int qh, qw;
                         p.fd_tw.divmod(row, qh, qw);
                         yok = row < p.th * p.tw && c.h0 + qh < p.img_h && c.w0 + qw < p.img_w;
@@ -495,7 +617,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const int cg = n0 + g * gw;
                     if (cg >= p.N) break;
                     const uint32_t src = stg + g * 16384;
-                    if (AM == LD_CONV) {
+                    if (AM == LD_CONV || AM == LD_CONV_HALO) {
                         ptx::tma_store_4d(&map_d, src, cg, c.w0, c.h0, c.n_i);
                     } else if (p.wgrad) {
                         if (p.split_ws) ptx::tma_store_4d(&map_d, src, cg, c.tap, c.m_t * kBlockM, c.split);
@@ -518,7 +640,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // per-CTA totals live in smem until the kernel ends (one global atomic per column per CTA).
             if ((p.stats != nullptr || EPI == 2) && !(p.dbg & (4 | 32))) {
                 int rlim = kBlockM;
-                constexpr bool conv_tile = (AM == LD_CONV);
+                constexpr bool conv_tile = (AM == LD_CONV) || (AM == LD_CONV_HALO);
                 if (conv_tile) rlim = p.th * p.tw;
                 else rlim = min(kBlockM, p.M - c.m_t * kBlockM);
                 float sa[8], sq[8];
@@ -841,9 +963,20 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     // bytes actually delivered per stage (full boxes, OOB elements are zero-filled and counted)
     uint32_t a_tx = p.a_bytes, b_tx = p.b_bytes;
     if (conv && !wgrad) a_tx = p.th * p.tw * 128;
+    const bool halo = conv && !wgrad && g->conv_halo != 0;
+    if (halo) {
+        if (p.taps != 9 || p.tw != 8 || p.th * p.tw != kBlockM)
+            return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: the halo form needs a 3x3 conv and a 16 x 8 pixel tile (got %d x %d)", p.th, p.tw);
+        p.halo_pitch = p.tw + 2;
+        a_tx = (p.th + 2) * (p.tw + 2) * 128;
+        p.a_stage_bytes = (a_tx + 1023) / 1024 * 1024;
+        p.a_stages = 3;
+        p.a_bytes = 0;           // the operand ring below holds the per-tap weight tiles only
+    }
     p.a_tx = a_tx;
     p.b_tx = b_tx;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const uint32_t halo_bytes = halo ? p.a_stages * p.a_stage_bytes : 0;
     const bool out_f32 = g->out_dtype == TRIS_DT_F32;
     if (out_f32 && bn > 128) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: fp32 output needs block_n <= 128 (staging)");
     if (conv && !wgrad && out_f32) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: conv forward/dgrad output is bf16");
@@ -868,14 +1001,23 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     if (smem_cap == 0) { const char* e = getenv("TRIS_GEMM_SMEM_KB"); smem_cap = (e && atoi(e) >= 64 && atoi(e) <= 227) ? atoi(e) * 1024u : 227u * 1024u; }
     const uint32_t fixed = 1024 + sizeof(SmemCtl) + 64 + p.stats_bytes;
     // two staging buffers (store of tile i overlaps the epilogue of tile i+1) when >= 4 pipeline stages still fit
-    p.nstg = (smem_cap - fixed - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
+    p.nstg = (smem_cap - fixed - halo_bytes - 2 * p.staging_bytes) / stage_bytes >= 4 ? 2 : 1;
     if (inorm) p.nstg = 1;     // the tile is normalised in place in its staging buffer
-    const uint32_t budget = smem_cap - fixed - p.nstg * p.staging_bytes;
+    const uint32_t budget = smem_cap - fixed - halo_bytes - p.nstg * p.staging_bytes;
     p.stages = budget / stage_bytes;
-    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages > kRingStages) p.stages = kRingStages;
     { const char* e = getenv("TRIS_GEMM_STAGES"); if (e && atoi(e) >= 2 && (uint32_t)atoi(e) < p.stages) p.stages = atoi(e); }
     if (p.stages < 2) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stage too large (%u bytes)", stage_bytes);
-    const size_t smem_bytes = fixed + p.stages * stage_bytes + p.nstg * p.staging_bytes;
+    p.b_stationary = 0;
+    if (halo && p.cblocks == 1 && p.tiles_n == 1 && kMaxStages >= 9) {
+        // weight-stationary: all nine taps fit next to the halo ring -> loaded once per CTA instead of once per tile
+        const uint32_t need = halo_bytes + 9 * stage_bytes;
+        uint32_t nst = p.nstg;
+        if (fixed + need + nst * p.staging_bytes > smem_cap) nst = 1;
+        if (fixed + need + nst * p.staging_bytes <= smem_cap) { p.b_stationary = 1; p.stages = 9; p.nstg = nst; }
+    }
+    p.ring_bytes = halo_bytes + p.stages * stage_bytes;
+    const size_t smem_bytes = fixed + p.ring_bytes + p.nstg * p.staging_bytes;
 
     p.fd_tiles_n = make_fastdiv(p.tiles_n); p.fd_tiles_m = make_fastdiv(p.tiles_m); p.fd_tiles_tap = make_fastdiv(p.tiles_tap);
     p.fd_split = make_fastdiv(p.split_k); p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
@@ -909,7 +1051,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
         if (C % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: conv channels %d %% 8", C);
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.img_w, (uint64_t)p.img_h, (uint64_t)p.img_n};
         uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)p.img_w * C * 2, (uint64_t)p.img_h * p.img_w * C * 2};
-        uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        uint32_t box[4] = {64, (uint32_t)(p.tw + (halo ? 2 : 0)), (uint32_t)(p.th + (halo ? 2 : 0)), 1};
         ma = tris::tensor_map_bf16(g->a, 4, dims, str, box);
     } else if (g->a_mode == TRIS_OP_K2D) {
         if (g->lda % 8) return tris::fail(TRIS_ERR_ALIGN, "tris_gemm: lda %d %% 8", g->lda);
@@ -994,7 +1136,7 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     }
 
     int am = LD_K2D, bm = LD_K2D;
-    if (conv && !wgrad) am = LD_CONV; else if (wgrad) am = LD_CONV_WG; else if (g->a_mode == TRIS_OP_MN2D) am = LD_MN2D;
+    if (halo) am = LD_CONV_HALO; else if (conv && !wgrad) am = LD_CONV; else if (wgrad) am = LD_CONV_WG; else if (g->a_mode == TRIS_OP_MN2D) am = LD_MN2D;
     if (wgrad) bm = LD_CONV_WG; else if (g->b_mode == TRIS_OP_MN2D) bm = (conv ? LD_MN2D_TAPS : LD_MN2D);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
     KernelFn fn = nullptr;
@@ -1007,6 +1149,8 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     else if (am == LD_CONV && bm == LD_K2D) fn = TRIS_PICK(LD_CONV, LD_K2D);
     else if (am == LD_CONV && bm == LD_MN2D_TAPS) fn = TRIS_PICK(LD_CONV, LD_MN2D_TAPS);
     else if (am == LD_CONV_WG && bm == LD_CONV_WG) fn = tris_umma_gemm_kernel<LD_CONV_WG, LD_CONV_WG, 0>;
+    else if (am == LD_CONV_HALO && bm == LD_K2D && !epi) fn = tris_umma_gemm_kernel<LD_CONV_HALO, LD_K2D, 0>;
+    else if (am == LD_CONV_HALO && bm == LD_MN2D_TAPS && !epi) fn = tris_umma_gemm_kernel<LD_CONV_HALO, LD_MN2D_TAPS, 0>;
     else return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: unsupported operand mode combination a=%d b=%d", g->a_mode, g->b_mode);
 #undef TRIS_PICK
     if (epi && (am == LD_MN2D || am == LD_CONV_WG)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: BatchNorm-backward epilogue needs a K-major / conv A operand");

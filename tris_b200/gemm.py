@@ -274,6 +274,13 @@ def conv_tile(h: int, w: int, max_rows: int = 128, mult: int = 1):
     return best
 
 
+CONV_HALO = os.environ.get("TRIS_CONV_HALO", "1") != "0"    # halo re-use for 3x3 convs whose images tile into 16 x 8 patches
+
+
+def _halo_ok(h, w, taps):
+    return CONV_HALO and taps == 9 and h % 16 == 0 and w % 8 == 0
+
+
 def conv3x3_fwd(x, wp, stats=None, out=None, block_n=None, taps=9):
     """y[n,h,w,co] = conv3x3(x[n,h,w,ci], pad 1, stride 1); wp packed [co, taps*ci]. taps=1 -> 1x1 conv via TMA-4D."""
     _chk(x, torch.bfloat16, "x"); _chk(wp, torch.bfloat16, "wp")
@@ -282,12 +289,13 @@ def conv3x3_fwd(x, wp, stats=None, out=None, block_n=None, taps=9):
     assert wp.shape[1] == taps * ci and ci % 64 == 0
     if out is None:
         out = torch.empty((n, h, w, co), device=x.device, dtype=torch.bfloat16)
-    th, tw = conv_tile(h, w)
+    halo = _halo_ok(h, w, taps)
+    th, tw = (16, 8) if halo else conv_tile(h, w)
     tiles_m = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
     bn = block_n or _bn_for(co, tiles_m)
     d = _desc(a=L.ptr(x), b=L.ptr(wp), d=L.ptr(out), stats=L.ptr(stats), a_mode=L.OP_CONV, b_mode=L.OP_K2D,
               M=n * h * w, N=co, K=taps * ci, ldb=taps * ci, ldd=co, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw,
-              taps=taps, block_n=bn, split_k=1, out_dtype=L.DT_BF16)
+              taps=taps, block_n=bn, split_k=1, out_dtype=L.DT_BF16, conv_halo=int(halo))
     L.gemm_raw(d)
     return out
 
@@ -299,12 +307,13 @@ def conv3x3_dgrad(dy, wp, cin, out=None, block_n=None, bwd_stats=None):
     assert wp.shape == (co, 9 * cin) and co % 64 == 0
     if out is None:
         out = torch.empty((n, h, w, cin), device=dy.device, dtype=torch.bfloat16)
-    th, tw = conv_tile(h, w)
+    halo = _halo_ok(h, w, 9) and bwd_stats is None
+    th, tw = (16, 8) if halo else conv_tile(h, w)
     tiles_m = n * ((h + th - 1) // th) * ((w + tw - 1) // tw)
     bn = block_n or _bn_for(cin, tiles_m, True)
     d = _desc(**_bwd_stats(dict(a=L.ptr(dy), b=L.ptr(wp), d=L.ptr(out), a_mode=L.OP_CONV, b_mode=L.OP_MN2D, M=n * h * w, N=cin,
               K=9 * co, ldb=9 * cin, ldd=cin, img_n=n, img_h=h, img_w=w, tile_h=th, tile_w=tw, taps=9, flip=1,
-              b_tap_stride=cin, block_n=bn, split_k=1, out_dtype=L.DT_BF16), bwd_stats))
+              b_tap_stride=cin, block_n=bn, split_k=1, out_dtype=L.DT_BF16, conv_halo=int(halo)), bwd_stats))
     L.gemm_raw(d)
     return out
 
