@@ -70,6 +70,8 @@ struct KParams {
     // a function of the absolute smem address -- tools/micro/umma_shift.cu)
     uint32_t a_stages, a_stage_bytes, halo_pitch;   // ring depth, bytes per halo tile (1024-aligned), tw + 2
     uint32_t ring_bytes;             // bytes of all operand rings (staging starts there)
+    int ng;                          // epilogue warp groups (1 or 2): with 2, the two groups of four warps drain ALTERNATING tiles,
+                                     // so the latency chain of one tile's epilogue overlaps the other's (short-K GEMMs)
     int b_stationary;                // halo form, 64 input channels, one N tile: the nine weight tiles are loaded ONCE per CTA
     int split_ws;                    // 1 = split-K partials leave through plain TMA stores into a [split][...] workspace
     const unsigned char* res_bits;   // optional [M, N/8]: residual added only where its bit is set
@@ -183,7 +185,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         for (int b = 0; b < kMaxAcc; ++b) {
             ptx::mbar_init(ptx::smem_u32(&ctl->acc_full[b]), 1);
-            ptx::mbar_init(ptx::smem_u32(&ctl->acc_empty[b]), 8);
+            ptx::mbar_init(ptx::smem_u32(&ctl->acc_empty[b]), 8 / p.ng);   // the warps of ONE epilogue group release a buffer
         }
         ptx::fence_mbar_init();
     }
@@ -446,24 +448,31 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // edge-clipped; fp32 weight gradients use TMA reduce-add instead of atomics).
         const int ew = warp - 2;
         const int q = warp & 3;
-        const int half = ew >> 2;
-        const int tid_e = threadIdx.x - 64;
+        const int ng = p.ng;                              // 1: all eight warps per tile; 2: four warps per tile, alternating tiles
+        const int GT = 256 / ng;                          // threads per group
+        const int grp = ng == 2 ? (ew >> 2) : 0;
+        const int half = ng == 2 ? 0 : (ew >> 2);         // one group: the two warps of a lane quadrant split the chunks
+        const int chstep = ng == 2 ? 1 : 2;
+        const int tid_e = ng == 2 ? ((threadIdx.x - 64) & 127) : (threadIdx.x - 64);   // thread index inside the group
+        const bool lead = (ng == 2 ? (ew & 3) : ew) == 0; // first warp of the group (its elected lane owns the TMA stores)
+        const uint32_t bar_id = 1 + grp;
         const int row = q * 32 + lane;
         const uint32_t stg0 = smem_base + p.ring_bytes;
-        float* s_stats = reinterpret_cast<float*>(smem + p.ring_bytes + p.nstg * p.staging_bytes);
+        // per group: [2N] running column sums, then the scratch of the statistics pass
+        float* s_stats = reinterpret_cast<float*>(smem + p.ring_bytes + p.nstg * p.staging_bytes) + grp * (p.stats_bytes / (4 * ng));
         const int esz = p.out_f32 ? 4 : 2;
         const int gw = 128 / esz;                      // columns per 128-byte staging group
         const int ngroups = (p.bn * esz) / 128;
         if (p.stats != nullptr) {
-            for (int i = tid_e; i < 2 * p.N; i += 256) s_stats[i] = 0.f;
+            for (int i = tid_e; i < 2 * p.N; i += GT) s_stats[i] = 0.f;
         }
         // statistics mapping (tile-invariant): thread = (16-byte vector of 8 columns, row part)
         const int nvec = p.bn >> 3;
-        const int vec = tid_e % nvec, part = tid_e / nvec, nparts = 256 / nvec;
+        const int vec = tid_e % nvec, part = tid_e / nvec, nparts = GT / nvec;
         const int rpp = kBlockM / nparts;
         uint32_t acc_phase = 0;
-        int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int it = grp;
+        for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += ng * gridDim.x, it += ng) {
             const TileCoord c = decode_tile(p, t);
             const int buf = it & (p.nacc - 1);
             const uint32_t stg = stg0 + (p.nstg == 2 ? (it & 1) * p.staging_bytes : 0);
@@ -474,18 +483,19 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // issuer threads); the named barrier then releases the other epilogue warps.
             // (elected lane of the first epilogue warp: elect.sync always picks the same lane, which therefore also owns the
             // bulk async-groups of the TMA stores below)
-            if (ew == 0 && ptx::elect_one()) {
+            if (lead && ptx::elect_one()) {
                 if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[4 * 64 + it] = clock64();
                 ptx::mbar_wait(ptx::smem_u32(&ctl->acc_full[buf]), (acc_phase >> buf) & 1);
                 if ((p.dbg & 8) && blockIdx.x == 0 && it < 64) p.dbg_buf[5 * 64 + it] = clock64();
                 // the TMA stores that last used this staging buffer have finished reading it
-                if (p.nstg == 2) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0();
+                // (two groups: each owns one staging buffer and its own bulk groups)
+                if (p.nstg == 2 && ng == 1) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0();
             }
             acc_phase ^= 1u << buf;
-            ptx::named_bar_sync(1, 256);
+            ptx::named_bar_sync(bar_id, GT);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
-            for (int ch = half; ch < ((p.dbg & 4) ? 0 : p.bn / 32); ch += 2) {
+            for (int ch = half; ch < ((p.dbg & 4) ? 0 : p.bn / 32); ch += chstep) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(taddr + ch * 32, raw);
                 ptx::tmem_ld_wait();
@@ -609,10 +619,10 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->acc_empty[buf]));
             ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(1, 256);
+            ptx::named_bar_sync(bar_id, GT);
             // ---- TMA store (one elected thread), issued BEFORE the statistics pass: both only read the staged tile, so the
             // store drains while the epilogue warps accumulate the column sums
-            if (ew == 0 && !(p.dbg & (4 | 64)) && ptx::elect_one()) {
+            if (lead && !(p.dbg & (4 | 64)) && ptx::elect_one()) {
                 for (int g = 0; g < ngroups; ++g) {
                     const int cg = n0 + g * gw;
                     if (cg >= p.N) break;
@@ -687,13 +697,13 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                 }
-                float* scr = s_stats + (EPI == 2 ? 2 * p.bn : 2 * p.N);   // [nparts][2][bn]
+                float* scr = s_stats + (EPI == 2 ? 2 * p.bn : 2 * p.N);   // [nparts][2][bn] (inside this group's region)
                 float* dst = scr + (part * 2) * p.bn + vec * 8;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { dst[i] = sa[i]; dst[p.bn + i] = sq[i]; }
-                ptx::named_bar_sync(1, 256);
+                ptx::named_bar_sync(bar_id, GT);
                 if (EPI != 2) {
-                    for (int jx = tid_e; jx < 2 * p.bn; jx += 256) {
+                    for (int jx = tid_e; jx < 2 * p.bn; jx += GT) {
                         int which, col;
                         p.fd_bn.divmod(jx, which, col);
                         if (n0 + col < p.N) {
@@ -706,7 +716,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     // ---- tile-local InstanceNorm (model/attn.py:75-105): this tile holds ALL pixels of one image for bn
                     // channels, so mean / biased variance over the pixels are complete here.  s_stats[0..bn) = scale
                     // (gamma * invstd), s_stats[bn..2bn) = shift (beta - mean * scale); mean / invstd saved for backward.
-                    for (int col = tid_e; col < p.bn; col += 256) {
+                    for (int col = tid_e; col < p.bn; col += GT) {
                         if (n0 + col < p.N) {
                             float sum = 0.f, sq = 0.f;
                             for (int pp = 0; pp < nparts; ++pp) { sum += scr[(pp * 2) * p.bn + col]; sq += scr[(pp * 2 + 1) * p.bn + col]; }
@@ -722,8 +732,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                     // the raw tile's TMA store must have finished READING the staging buffer before it is normalised in place
-                    if (ew == 0 && ptx::elect_one()) ptx::bulk_wait_read0();
-                    ptx::named_bar_sync(1, 256);
+                    if (lead && ptx::elect_one()) ptx::bulk_wait_read0();
+                    ptx::named_bar_sync(bar_id, GT);
                     if (scol < p.N) {
                         float sc8[8], sh8[8];
 #pragma unroll
@@ -758,8 +768,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                     ptx::fence_proxy_async_smem();
-                    ptx::named_bar_sync(1, 256);
-                    if (ew == 0 && ptx::elect_one()) {
+                    ptx::named_bar_sync(bar_id, GT);
+                    if (lead && ptx::elect_one()) {
                         for (int g = 0; g < ngroups; ++g) {
                             const int cg = n0 + g * gw;
                             if (cg >= p.N) break;
@@ -771,18 +781,27 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             if ((p.dbg & 8) && blockIdx.x == 0 && tid_e == 0 && it < 64) p.dbg_buf[6 * 64 + it] = clock64();
         }
-        if (ew == 0 && ptx::elect_one()) ptx::bulk_wait_all();
+        if (lead && ptx::elect_one()) ptx::bulk_wait_all();
         if (p.stats != nullptr) {
             // deterministic: every CTA stores its partial sums as row blockIdx.x of stats[stats_parts][2N] (tiles are
             // assigned statically, sums inside a CTA run in a fixed order); the consumer adds the rows in order.
             // Rows no CTA owns (grid smaller than stats_parts) are cleared here.
-            ptx::named_bar_sync(1, 256);
+            ptx::named_bar_sync(bar_id, GT);
             float* dst = p.stats + static_cast<long>(blockIdx.x) * 2 * p.N;
-            for (int i = tid_e; i < 2 * p.N; i += 256) dst[i] = s_stats[i];
-            for (int r = gridDim.x + blockIdx.x; r < p.stats_parts; r += gridDim.x) {
-                float* z = p.stats + static_cast<long>(r) * 2 * p.N;
-                for (int i = tid_e; i < 2 * p.N; i += 256) z[i] = 0.f;
+            if (ng == 2) {
+                // the two groups accumulated separately: meet on a CTA-wide named barrier, group 0 adds (fixed order)
+                ptx::named_bar_sync(3, 256);
+                const float* other = s_stats + p.stats_bytes / 8;
+                if (grp == 0)
+                    for (int i = tid_e; i < 2 * p.N; i += GT) dst[i] = s_stats[i] + other[i];
+            } else {
+                for (int i = tid_e; i < 2 * p.N; i += GT) dst[i] = s_stats[i];
             }
+            if (grp == 0)
+                for (int r = gridDim.x + blockIdx.x; r < p.stats_parts; r += gridDim.x) {
+                    float* z = p.stats + static_cast<long>(r) * 2 * p.N;
+                    for (int i = tid_e; i < 2 * p.N; i += GT) z[i] = 0.f;
+                }
         }
     }
     ptx::tc_fence_before();
@@ -993,7 +1012,9 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     if (g->mask_sc && batch > 1) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: mask epilogue is for the non-batched modes");
     p.staging_bytes = bn * (out_f32 ? 4 : 2) * 128;
     if (p.staging_bytes < 16384) p.staging_bytes = 16384;
-    p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 + 16384 : 0;
+    // column statistics: [2N] running sums + 16 KB scratch; with N <= 1024 room for a second copy of the sums, so that two
+    // epilogue groups (p.ng == 2) can each own [2N sums][8 KB scratch]
+    p.stats_bytes = g->stats ? ((2 * g->N * 4 + 1023) / 1024) * 1024 * (g->N <= 1024 ? 2 : 1) + 16384 : 0;
     if (inorm) p.stats_bytes = ((2 * bn * 4 + 1023) / 1024) * 1024 + 16384;
     p.nacc = 512 / bn >= 4 ? 4 : 2;   // power of two (ring index = it & (nacc - 1))
     p.acc_stride = bn;
@@ -1008,6 +1029,15 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     if (p.stages > kRingStages) p.stages = kRingStages;
     { const char* e = getenv("TRIS_GEMM_STAGES"); if (e && atoi(e) >= 2 && (uint32_t)atoi(e) < p.stages) p.stages = atoi(e); }
     if (p.stages < 2) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: stage too large (%u bytes)", stage_bytes);
+    // two epilogue groups on alternating tiles: plain epilogue, two staging buffers, more than one tile per CTA
+    p.ng = 1;
+    {
+        static int ng_env = -1;
+        if (ng_env < 0) { const char* e = getenv("TRIS_GEMM_NG"); ng_env = e ? atoi(e) : 2; }
+        const long tiles_all = static_cast<long>(p.tiles_tap) * p.tiles_m * p.tiles_n * p.split_k * p.batch;
+        const bool stats_ok = !g->stats || g->N <= 1024;
+        if (ng_env == 2 && !inorm && g->stats_mode != 1 && !g->mask_sc && p.nstg == 2 && tiles_all > tris::sm_count() && stats_ok) p.ng = 2;
+    }
     p.b_stationary = 0;
     if (halo && p.cblocks == 1 && p.tiles_n == 1 && kMaxStages >= 9) {
         // weight-stationary: all nine taps fit next to the halo ring -> loaded once per CTA instead of once per tile
