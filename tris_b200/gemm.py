@@ -20,10 +20,18 @@ SMS = 148
 _KBLOCK_US = {32: 0.17, 64: 0.20, 128: 0.27, 256: 0.45}
 
 
-def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False) -> int:
-    """UMMA N per tile: the width that minimises  waves(148 SMs) x (time of one k-block at that width)."""
+# measured: isolated short-K GEMMs gain 8-20 % with 128-wide tiles, the whole step LOSES 0.2 ms (more A re-reads) -> off
+SHORTK_BN128 = os.environ.get("TRIS_BN_SHORTK", "0") == "1"
+
+
+def _bn_for(n: int, tiles_m: int, mn_major_b: bool = False, k: int = 0) -> int:
+    """UMMA N per tile: the width that minimises  waves(148 SMs) x (time of one k-block at that width).
+    Short contractions (k <= 128: one or two k-blocks per tile) are bound by the epilogue, not the mainloop: 128-wide
+    tiles leave room for two staging buffers, so that the two epilogue groups can overlap consecutive tiles."""
     if n <= 32 and not mn_major_b:
         return 32
+    if SHORTK_BN128 and 0 < k <= 128 and n >= 128 and tiles_m * ((n + 127) // 128) > 2 * SMS:
+        return 128
     n_pad = ((n + 63) // 64) * 64
     best, best_cost = 64, None
     for bn in (64, 128, 256):
@@ -155,7 +163,7 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
     if out is None:
         out = torch.empty((m, n), device=x.device, dtype=out_dtype)
     tiles_m = (m + 127) // 128
-    bn = block_n or _bn_for(n, tiles_m)
+    bn = block_n or _bn_for(n, tiles_m, k=k)
     if out.dtype == torch.float32:
         bn = min(bn, 128)
     d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(out), bias=L.ptr(bias), residual=L.ptr(residual), stats=L.ptr(stats),
@@ -197,7 +205,7 @@ def linear_dgrad(dy, w, out=None, out_dtype=torch.bfloat16, residual=None, block
     if out is None:
         out = torch.empty((m, k), device=dy.device, dtype=out_dtype)
     tiles_m = (m + 127) // 128
-    bn = block_n or _bn_for(k, tiles_m, True)
+    bn = block_n or _bn_for(k, tiles_m, True, k=n)
     if out.dtype == torch.float32:
         bn = min(bn, 128)
     d = _desc(**_bwd_stats(dict(a=L.ptr(dy), b=L.ptr(w), d=L.ptr(out), residual=L.ptr(residual), bias=L.ptr(bias), a_mode=L.OP_K2D,
