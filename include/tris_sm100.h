@@ -137,22 +137,24 @@ int tris_splitk_reduce_multi(const tris_reduce_item* items, int n, tris_stream_t
  * (downsample) -- CLIP/clip/model.py:18-28,36-40,42-55.  fold_half = c/2: channels c and c + c/2 are one BatchNorm channel
  * (image-pair-packed stem).  save_scale0 / save_shift0 (optional, [C]): gamma*invstd and beta - mean*gamma*invstd of branch 0,
  * kept for the backward GEMM epilogues that recompute the ReLU mask from y.  relu_bits (optional, uint8 [rows, C/8]): sign bits
- * of the output, so that the backward pass masks gradients without re-reading the bf16 output. */
+ * of the output, so that the backward pass masks gradients without re-reading the bf16 output.  unpair (pool 2 only): the two
+ * channel halves are the two images of a pair; the output is written un-paired as [2n, h/2, w/2, c/2]. */
 int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, const float* beta0, float* rm0,
     float* rv0, float* save_mean0, float* save_invstd0, const void* y1, const float* stats1, const float* gamma1,
     const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1, const void* residual, void*
     out, int n, int h, int w, int c, int pool, int relu, int train, float momentum, float eps, int stats_parts,
-    int fold_half, float* save_scale0, float* save_shift0, void* relu_bits, tris_stream_t stream);
+    int fold_half, float* save_scale0, float* save_shift0, void* relu_bits, int unpair, tris_stream_t stream);
 /* backward of the above: per-channel reductions (two-stage, fixed order: partial rows in `ws`, then a finalize kernel
  * that also adds into dgamma / dbeta) then dy (and the residual gradient g_out) -- model.py:42-55.  ws holds
  * [nparts][K][C] partial rows + [K][C] finalized sums (K = 3 with a second branch, else 2); ext_parts > 0: the rows were
  * written by the GEMM that produced `dout` (tris_gemm stats_mode 1) and `dout` is already the masked gradient.
- * relu_bits (optional): the mask written by tris_bn_apply_fwd, used instead of `out`. */
+ * relu_bits (optional): the mask written by tris_bn_apply_fwd, used instead of `out`.  unpair (pool 2 only): dout is the
+ * un-paired [2n, h/2, w/2, c/2] gradient of the forward's un-paired output. */
 int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* gamma0, const float* beta0, const
     float* save_mean0, const float* save_invstd0, float* dgamma0, float* dbeta0, void* dy0, const void* y1, const
     float* gamma1, const float* beta1, const float* save_mean1, const float* save_invstd1, float* dgamma1, float*
     dbeta1, void* dy1, void* g_out, int n, int h, int w, int c, int pool, int relu, int fold_half, float* ws,
-    long ws_floats, int ext_parts, const void* relu_bits, tris_stream_t stream);
+    long ws_floats, int ext_parts, const void* relu_bits, int unpair, tris_stream_t stream);
 /* nn.AvgPool2d(2) on NHWC bf16 (the anti-aliased stride of the downsample branch, model.py:37). */
 int tris_avgpool2_fwd(const void* x, void* out, int n, int h, int w, int c, tris_stream_t stream);
 /* its adjoint (+ optional accumulate source). */

@@ -114,6 +114,25 @@ def test_bn_apply_and_backward(K, c, pool, mode):
             assert torch.equal(dy1_b, dy1)
 
 
+def test_bn_pooled_unpair_layout(K):
+    """Pair-packed stem (images 2i, 2i+1 share a row as channel halves): the pooled apply kernel writes the un-paired
+    [2n, h/2, w/2, c/2] layout itself and the backward kernels read the un-paired gradient -- bit-identical to the explicit
+    permute copies they replace."""
+    n, h, w, c = 3, 12, 8, 128
+    y = rnd(n, h, w, c, seed=11, shift=0.3)
+    bn_a, bn_b = make_bn(K, c, 12), make_bn(K, c, 12)
+    paired = K.bn_apply(y, stats_of(y), bn_a, True, relu=True, pool=2, fold_half=64)
+    unp = K.bn_apply(y, stats_of(y), bn_b, True, relu=True, pool=2, fold_half=64, unpair=True)
+    assert unp.shape == (2 * n, h // 2, w // 2, c // 2)
+    want = paired.view(n, h // 2, w // 2, 2, 64).permute(0, 3, 1, 2, 4).reshape(2 * n, h // 2, w // 2, 64)
+    assert torch.equal(unp, want)
+    dout = rnd(2 * n, h // 2, w // 2, 64, seed=13)
+    dpaired = dout.reshape(n, 2, h // 2, w // 2, 64).permute(0, 2, 3, 1, 4).reshape(n, h // 2, w // 2, 128).contiguous()
+    dy_a, _, _ = K.bn_bwd(dpaired, None, y, bn_a, pool=2, fold_half=64)
+    dy_b, _, _ = K.bn_bwd(dout, None, y, bn_b, pool=2, fold_half=64, unpair=True)
+    assert torch.equal(dy_a, dy_b) and torch.equal(bn_a.dgamma, bn_b.dgamma) and torch.equal(bn_a.dbeta, bn_b.dbeta)
+
+
 def test_bn_eval_mode(K):
     y = rnd(2, 8, 8, 128, seed=1)
     bn = make_bn(K, 128, 2)

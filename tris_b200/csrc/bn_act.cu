@@ -81,6 +81,7 @@ struct ApplyParams {
     unsigned char* relu_bits; // optional [M_out, C/8]: bit i of byte (row, c/8) = (out[row, c + i] > 0); lets the backward
                               // kernels mask the upstream gradient without re-reading the bf16 output (1/16 of its bytes)
     int n, h, w, c, pool, relu, train;
+    int unpair;                  // pooled form only: channel halves are the two images of a pair -> write out as [2n, ho, wo, c/2]
     float count, momentum, eps;
 };
 
@@ -271,7 +272,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
                     }
                 }
         }
-        st8(p.out + orow * p.c + c0, acc);
+        if (p.unpair) {       // (pair ni, channel half j) -> image 2 ni + j with c/2 channels
+            const int half = p.c >> 1, j = c0 >= half;
+            const long hw = static_cast<long>(ho) * wo;
+            const long ni = orow / hw, rem = orow - ni * hw;
+            st8(p.out + ((2 * ni + j) * hw + rem) * half + (c0 - j * half), acc);
+        } else {
+            st8(p.out + orow * p.c + c0, acc);
+        }
         if (p.relu_bits != nullptr) {
             unsigned b = 0;
 #pragma unroll
@@ -294,6 +302,7 @@ struct BwdParams {
     __nv_bfloat16* dy0; __nv_bfloat16* dy1;   // [M_in, C]
     __nv_bfloat16* g_out;        // optional [M_out, C]: masked upstream gradient (identity branch)
     int n, h, w, c, pool, relu;
+    int unpair;                  // pooled form only: dout is [2n, ho, wo, c/2] (un-paired images), read as the pair-packed [n, ho, wo, c]
     float count;
 };
 
@@ -309,7 +318,15 @@ __device__ __forceinline__ Vec8 lds8(const float* s) {
 // g at output row orow for channel group c0, masked (ReLU) and pool-scaled.  sc/sh: smem scale/shift of branch 0 (mask
 // recompute when the forward output was not kept).
 __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long orow, int c0, const Vec8& y0, const float* s_sc, const float* s_sh) {
-    Vec8 g = ld8(p.dout + orow * p.c + c0);
+    Vec8 g;
+    if (p.unpair) {
+        const int half = p.c >> 1, j = c0 >= half;
+        const long hw = static_cast<long>(p.h / 2) * (p.w / 2);
+        const long ni = orow / hw, rem = orow - ni * hw;
+        g = ld8(p.dout + ((2 * ni + j) * hw + rem) * half + (c0 - j * half));
+    } else {
+        g = ld8(p.dout + orow * p.c + c0);
+    }
     if (p.pool == 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g.v[i] *= 0.25f;
@@ -575,7 +592,7 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
                       const float* beta1, float* rm1, float* rv1, float* save_mean1, float* save_invstd1,
                       const void* residual, void* out, int n, int h, int w, int c, int pool, int relu, int train,
                       float momentum, float eps, int stats_parts, int fold_half, float* save_scale0, float* save_shift0,
-                      void* relu_bits, tris_stream_t stream) {
+                      void* relu_bits, int unpair, tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_apply_fwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pool must be 1 or 2");
     if (pool == 2 && (y1 || residual || (h & 1) || (w & 1))) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: pooled form is single-branch, even h/w");
@@ -589,7 +606,8 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.relu_bits = reinterpret_cast<unsigned char*>(relu_bits);
     if (relu_bits && (pool != 1 || !relu)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: relu_bits needs relu, pool 1");
-    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = relu; p.train = train;
+    if (unpair && (pool != 2 || c % 16)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_apply_fwd: unpair needs pool 2, c %% 16 == 0");
+    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = relu; p.train = train; p.unpair = unpair;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     p.momentum = momentum; p.eps = eps;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -624,7 +642,7 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
                 const void* y1, const float* gamma1, const float* beta1, const float* save_mean1,
                 const float* save_invstd1, float* dgamma1, float* dbeta1, void* dy1, void* g_out, int n, int h, int w,
                 int c, int pool, int relu, int fold_half, float* ws, long ws_floats, int ext_parts,
-                const void* relu_bits, tris_stream_t stream) {
+                const void* relu_bits, int unpair, tris_stream_t stream) {
     if (int e = check_c(c, "tris_bn_bwd")) return e;
     if (pool != 1 && pool != 2) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: pool must be 1 or 2");
     if (!ws) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: workspace required");
@@ -643,7 +661,8 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     p.dy0 = reinterpret_cast<__nv_bfloat16*>(dy0);
     p.dy1 = reinterpret_cast<__nv_bfloat16*>(dy1);
     p.g_out = reinterpret_cast<__nv_bfloat16*>(g_out);
-    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = ext_parts > 0 ? 0 : relu;
+    if (unpair && (pool != 2 || c % 16)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: unpair needs pool 2, c %% 16 == 0");
+    p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = ext_parts > 0 ? 0 : relu; p.unpair = unpair;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     p.kred = y1 ? 3 : 2;
     p.fold_half = fold_half;

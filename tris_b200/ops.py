@@ -41,18 +41,18 @@ STAT_PARTS = 148      # rows of a partial-statistics buffer: one per CTA of the 
 
 
 def bn_apply(y, stats, bn: BNState, train, relu=True, pool=1, y1=None, stats1=None, bn1: BNState = None, residual=None,
-             momentum=0.1, eps=1e-5, fold_half=0, bits=None):
+             momentum=0.1, eps=1e-5, fold_half=0, bits=None, unpair=False):
     """stats / stats1: the GEMM epilogue's partial rows [STAT_PARTS, 2C] (train mode); they are summed in a fixed order by
     the finalize kernel that precedes the apply kernel.  bits: optional uint8 [rows, C/8] receiving the sign bits of the output
     (the ReLU mask the backward kernels need, at 1/16 of the bytes of the output)."""
     n, h, w, c = y.shape
-    out = empty((n, h // pool, w // pool, c), y)
+    out = empty((2 * n, h // pool, w // pool, c // 2) if unpair else (n, h // pool, w // pool, c), y)
     L.call("tris_bn_apply_fwd", _vp(y), _vp(stats), _vp(bn.gamma), _vp(bn.beta), _vp(bn.rm), _vp(bn.rv), _vp(bn.mean),
            _vp(bn.invstd), _vp(y1), _vp(stats1), _vp(bn1.gamma if bn1 else None), _vp(bn1.beta if bn1 else None),
            _vp(bn1.rm if bn1 else None), _vp(bn1.rv if bn1 else None), _vp(bn1.mean if bn1 else None),
            _vp(bn1.invstd if bn1 else None), _vp(residual), _vp(out), n, h, w, c, pool, int(relu), int(train),
            C.c_float(momentum), C.c_float(eps), STAT_PARTS if train else 0, int(fold_half), _vp(bn.scale), _vp(bn.shift),
-           _vp(bits), launches=2 if train else 1)
+           _vp(bits), int(unpair), launches=2 if train else 1)
     return out
 
 
@@ -60,7 +60,7 @@ _BN_BWD_PARTS = 4 * 148     # CTAs of the reduction kernel (4 resident per SM)
 
 
 def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState = None, want_g=False, fold_half=0, ext=None,
-           bits=None):
+           bits=None, unpair=False):
     """Returns (dy, dy1|None, g|None); adds dgamma/dbeta into bn.dgamma/bn.dbeta (fp32).  The per-channel reductions are
     two-stage in a private workspace (never in the gradient buffers) and bit-reproducible.
     ext: partial rows [STAT_PARTS, 2C] (+ 2C spare floats) written by the GEMM that produced `dout` (gemm.py bwd_stats=):
@@ -78,7 +78,7 @@ def bn_bwd(dout, out, y, bn: BNState, relu=True, pool=1, y1=None, bn1: BNState =
            _vp(bn.dgamma), _vp(bn.dbeta), _vp(dy), _vp(y1), _vp(bn1.gamma if bn1 else None),
            _vp(bn1.beta if bn1 else None), _vp(bn1.mean if bn1 else None), _vp(bn1.invstd if bn1 else None),
            _vp(bn1.dgamma if bn1 else None), _vp(bn1.dbeta if bn1 else None), _vp(dy1), _vp(g), n, h, w, c, pool,
-           int(relu), int(fold_half), _vp(ws), C.c_long(ws.numel()), ext_parts, _vp(bits), launches=3 if ext is None else 2)
+           int(relu), int(fold_half), _vp(ws), C.c_long(ws.numel()), ext_parts, _vp(bits), int(unpair), launches=3 if ext is None else 2)
     return dy, dy1, g
 
 

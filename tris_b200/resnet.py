@@ -85,6 +85,7 @@ class ResNetTower:
         n_stats = 2 * (64 * 2 + 128 + sum(b.planes * 2 + b.planes * 4 * (2 if b.down else 1) for b in self.blocks))
         # BatchNorm batch statistics: every conv GEMM writes ops.STAT_PARTS partial rows of [2C] (one per CTA, fixed order)
         self.stats_buf = torch.zeros(n_stats * ops.STAT_PARTS, device=dev, dtype=f32)
+        self._pack_stream = self._pack_pending = None    # side stream of refresh() and its not-yet-joined work
         self._wgq = None             # gemm.SplitKQueue of a running backward() (None: split-K second stages run immediately)
         self._wg_post = []
         self._wg_stream = None
@@ -94,26 +95,58 @@ class ResNetTower:
 
     # ------------------------------------------------------------------ derived weights
     def refresh(self):
-        """Re-derive packed / padded bf16 operands from the fp32 masters (after an optimizer step or a load)."""
+        """Re-derive packed / padded bf16 operands from the fp32 masters (after an optimizer step or a load).
+        Only the stem operands are derived on the calling stream (5 small pack kernels + ONE multi-tensor copy); the sixteen
+        3x3 block weights are packed on a side stream next to the stem and joined by `forward` in front of layer 1
+        (profiles/r2_step_timeline_kernels.txt: the serial form was 0.17 ms at the head of every step)."""
+        from .engine import OVERLAP
         st, p = self.store, self.prefix
-        ops.pack_conv(st.p(p + "conv1.weight"), self._tmp27())          # [32, (r,s,c)] matches stem_im2col's k order
-        self.w_stem1[:32, :27].copy_(self._tmp27())
+        main = torch.cuda.current_stream()
+        if OVERLAP:
+            if self._pack_stream is None:
+                self._pack_stream = torch.cuda.Stream()
+            side = self._pack_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for blk in self.blocks:
+                    ops.pack_conv(st.p(blk.p + "conv2.weight"), self.w3x3[blk.p])
+            self._pack_pending = side
+        else:
+            for blk in self.blocks:
+                ops.pack_conv(st.p(blk.p + "conv2.weight"), self.w3x3[blk.p])
+        t27 = self._tmp27()
+        ops.pack_conv(st.p(p + "conv1.weight"), t27)                    # [32, (r,s,c)] matches stem_im2col's k order
         ops.pack_conv(st.p(p + "conv2.weight"), self.w_stem2, co_pad=64, ci_pad=64)
         ops.pack_conv(st.p(p + "conv3.weight"), self.w_stem3, co_pad=64, ci_pad=64)
-        for blk in self.blocks:
-            ops.pack_conv(st.p(blk.p + "conv2.weight"), self.w3x3[blk.p])
-        for k, pad in self.pad_bn.items():
-            real = self.real_small_bn[k]
-            pad.gamma[:32].copy_(real.gamma); pad.beta[:32].copy_(real.beta)
-            pad.rm[:32].copy_(real.rm); pad.rv[:32].copy_(real.rv)
-        self.w_pair1[:32, :27].copy_(self._tmp27())
-        self.w_pair1[32:, 32:59].copy_(self._tmp27())
         ops.pack_conv_blockdiag(st.p(p + "conv2.weight"), self.w_pair2)
         ops.pack_conv_blockdiag(st.p(p + "conv3.weight"), self.w_pair3)
+        dst, src = [self.w_stem1[:32, :27], self.w_pair1[:32, :27], self.w_pair1[32:, 32:59]], [t27, t27, t27]
+        for k, pad in self.pad_bn.items():
+            real = self.real_small_bn[k]
+            dst += [pad.gamma[:32], pad.beta[:32], pad.rm[:32], pad.rv[:32]]
+            src += [real.gamma, real.beta, real.rm, real.rv]
         for k, pr in self.pair_bn.items():
             real, c = self.pair_real[k], self.pair_real[k].gamma.numel()
-            for dst, src in ((pr.gamma, real.gamma), (pr.beta, real.beta), (pr.rm, real.rm), (pr.rv, real.rv)):
-                dst[:c].copy_(src); dst[c:].copy_(src)
+            for d, r in ((pr.gamma, real.gamma), (pr.beta, real.beta), (pr.rm, real.rm), (pr.rv, real.rv)):
+                dst += [d[:c], d[c:]]
+                src += [r, r]
+        self._copy_groups(dst, src)
+
+    @staticmethod
+    def _copy_groups(dst, src):
+        """Multi-tensor copy (layout only), one launch per dtype group instead of one per tensor."""
+        groups = {}
+        for d, r in zip(dst, src):
+            groups.setdefault((d.dtype, r.dtype, d.dim()), ([], []))
+            groups[(d.dtype, r.dtype, d.dim())][0].append(d)
+            groups[(d.dtype, r.dtype, d.dim())][1].append(r)
+        for d, r in groups.values():
+            torch._foreach_copy_(d, r)
+
+    def _join_packs(self):
+        if self._pack_pending is not None:
+            torch.cuda.current_stream().wait_stream(self._pack_pending)
+            self._pack_pending = None
 
     def _tmp27(self):
         if not hasattr(self, "_t27"):
@@ -146,7 +179,7 @@ class ResNetTower:
             x, stem_rec = self._stem_fwd_padded(img, train, stats)
         if train:
             tape["stem"] = (pair,) + stem_rec
-        feats = []
+        self._join_packs()
         for blk in self.blocks:
             x, rec = self._block_fwd(blk, x, train, stats)
             if train:
@@ -160,13 +193,15 @@ class ResNetTower:
         """The stem BatchNorms run on private padded / pair-packed copies of their parameters; after a train-mode forward
         the real running statistics (already updated) are mirrored into BOTH sets so that either stem path can follow."""
         p = self.prefix
+        dst, src = [], []
         for nm in ("bn1", "bn2"):
             pad, real = self.pad_bn[p + nm], self.real_small_bn[p + nm]
-            pad.rm[:32].copy_(real.rm); pad.rv[:32].copy_(real.rv)
+            dst += [pad.rm[:32], pad.rv[:32]]; src += [real.rm, real.rv]
         for nm in ("bn1", "bn2", "bn3"):
             pr, real = self.pair_bn[p + nm], self.pair_real[p + nm]
             c = real.rm.numel()
-            pr.rm[:c].copy_(real.rm); pr.rm[c:].copy_(real.rm); pr.rv[:c].copy_(real.rv); pr.rv[c:].copy_(real.rv)
+            dst += [pr.rm[:c], pr.rm[c:], pr.rv[:c], pr.rv[c:]]; src += [real.rm, real.rm, real.rv, real.rv]
+        self._copy_groups(dst, src)
 
     def _stem_fwd_padded(self, img, train, stats):
         """Odd batches: the two 32-channel activations are carried zero-padded to 64 channels."""
@@ -182,10 +217,9 @@ class ResNetTower:
         s3 = stats(64)
         y3 = G.conv3x3_fwd(a2, self.w_stem3, stats=s3)
         x = ops.bn_apply(y3, s3, self.bn[p + "bn3"], train, pool=2)
-        if train:
-            for nm in ("bn1", "bn2"):   # running stats of the padded copies back into the real buffers
-                pad, real = self.pad_bn[p + nm], self.real_small_bn[p + nm]
-                real.rm.copy_(pad.rm[:32]); real.rv.copy_(pad.rv[:32])
+        if train:   # running stats of the padded copies back into the real buffers
+            pads, reals = [self.pad_bn[p + nm] for nm in ("bn1", "bn2")], [self.real_small_bn[p + nm] for nm in ("bn1", "bn2")]
+            self._copy_groups([t for r in reals for t in (r.rm, r.rv)], [t for q in pads for t in (q.rm[:32], q.rv[:32])])
         return x, (col, y1, a1, y2, a2, y3)
 
     def _stem_fwd_pair(self, img, train, stats):
@@ -208,13 +242,15 @@ class ResNetTower:
         s3 = stats(128)
         with G.algo(0.5):
             y3 = G.conv3x3_fwd(a2, self.w_pair3, stats=s3)
-        xp = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2, fold_half=64 if train else 0)   # [B/2, H/4, W/4, 128]
-        x = xp.view(B2, H // 4, W // 4, 2, 64).permute(0, 3, 1, 2, 4).reshape(B, H // 4, W // 4, 64).contiguous()   # un-pair: layout only
+        # [B/2, H/4, W/4, 128] pair-packed -> written un-paired as [B, H/4, W/4, 64] by the same kernel
+        x = ops.bn_apply(y3, s3, self.pair_bn[p + "bn3"], train, pool=2, fold_half=64 if train else 0, unpair=True)
         if train:
+            dst, src = [], []
             for nm in ("bn1", "bn2", "bn3"):
                 pr, real = self.pair_bn[p + nm], self.pair_real[p + nm]
                 c = real.rm.numel()
-                real.rm.copy_(pr.rm[:c]); real.rv.copy_(pr.rv[:c])
+                dst += [real.rm, real.rv]; src += [pr.rm[:c], pr.rv[:c]]
+            self._copy_groups(dst, src)
         return x, (col, y1, a1, y2, a2, y3)
 
     def _block_fwd(self, blk: _Block, x, train, stats):
@@ -354,11 +390,8 @@ class ResNetTower:
         st, p = self.store, self.prefix
         B, h4, w4, _ = dout.shape
         B2 = B // 2
-        for nm in ("bn1", "bn2", "bn3"):
-            pr = self.pair_bn[p + nm]
-            pr.dgamma.zero_(); pr.dbeta.zero_()
-        dxp = dout.reshape(B2, 2, h4, w4, 64).permute(0, 2, 3, 1, 4).reshape(B2, h4, w4, 128).contiguous()   # re-pair: layout only
-        dy3, _, _ = ops.bn_bwd(dxp, None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64)
+        torch._foreach_zero_([t for nm in ("bn1", "bn2", "bn3") for t in (self.pair_bn[p + nm].dgamma, self.pair_bn[p + nm].dbeta)])
+        dy3, _, _ = ops.bn_bwd(dout.contiguous(), None, y3, self.pair_bn[p + "bn3"], pool=2, fold_half=64, unpair=True)   # re-pairs on read
         self._wgrad3x3_pair(dy3, a2, p + "conv3.weight")
         ext2, bs2 = self._bwd_stats(y2, self.pair_bn[p + "bn2"]) if FUSE_BN_BWD else (None, None)
         with G.algo(0.5):

@@ -67,6 +67,7 @@ class Stage1Trainer:
                  process_group=None):
         self.model, self.aux, self.w = model, aux, w
         self.eng = model.engine()
+        self._zero_stream = None
         st = self.eng.store
         self.m = torch.zeros(st.n_train, device=st.device, dtype=f32)
         self.v = torch.zeros(st.n_train, device=st.device, dtype=f32)
@@ -142,8 +143,15 @@ class Stage1Trainer:
 
     def _fwd_bwd(self, img, word_ids, neg_word_ids):
         self.model.train()
-        self.eng.store.zero_grad()
+        # clearing the 454 MB flat gradient buffer (61 us) runs next to the forward pass; joined in front of the backward pass
+        main = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream()
+        self._zero_stream.wait_stream(main)
+        with torch.cuda.stream(self._zero_stream):
+            self.eng.store.zero_grad()
         losses = stage1_losses(self.model, self.aux, img, word_ids, neg_word_ids, *self.w)
+        main.wait_stream(self._zero_stream)
         losses["loss"].backward()
         return losses
 
