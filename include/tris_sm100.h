@@ -113,6 +113,8 @@ typedef struct tris_gemm_desc {
     uint64_t* tstamp;     /* optional uint64[2], initialised {UINT64_MAX, 0}: the kernel leaves min(%globaltimer at CTA start)
                              and max(%globaltimer at CTA end) there -- the device-side duration of this launch, also inside
                              a CUDA-graph replay (measurement aid of bench.py; NULL in production) */
+    int32_t residual_f32; /* 1 = `residual` is fp32 [M, ldd] (the fp32 residual stream of the transformer towers; use with
+                             out_dtype F32); 0 = bf16 */
 } tris_gemm_desc;
 
 int tris_gemm(tris_gemm_desc* desc, tris_stream_t stream);
@@ -261,20 +263,22 @@ int tris_flag_inc(uint32_t* flag, tris_stream_t stream);
 int tris_flag_wait(const uint32_t* flag, uint32_t target, tris_stream_t stream);
 
 /* ---- transformer.cu */
-/* token_embedding[ids] + positional_embedding, EOT index = argmax(ids) (model.py:552-564). */
-int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D,
+/* token_embedding[ids] + positional_embedding, EOT index = argmax(ids) (model.py:552-564).  x_f32: x is fp32 -- the residual
+ * stream of a transformer stays in fp32 between blocks, as it does in the reference under autocast (fp32 embeddings +
+ * low-precision branch outputs promote to fp32); branch inputs (LayerNorm outputs) are bf16. */
+int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D, int x_f32,
     tris_stream_t stream);
 /* dE[ids] += dx, dP += sum_n dx: owner-computes (first occurrence of a token id adds all its occurrences in order), no
  * atomics. */
 int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, int L, int D, tris_stream_t stream);
-/* LayerNorm in fp32 (model.py:352-358). */
+/* LayerNorm in fp32 (model.py:352-358).  x_f32 / y_f32: input / output rows are fp32 instead of bf16. */
 int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int
-    rows, int D, float eps, tris_stream_t stream);
+    rows, int D, float eps, int x_f32, int y_f32, tris_stream_t stream);
 /* its backward (+ residual-gradient add).  ws (optional): fp32 [2][ws_rows][D] per-CTA partial rows of dgamma (plane 0) /
  * dbeta (plane 1) from exactly ws_rows CTAs (1 <= ws_rows <= ceil(rows / 8)); add them in order with
- * tris_splitk_reduce_multi (split = ws_rows). */
+ * tris_splitk_reduce_multi (split = ws_rows).  x_f32: the saved forward input x is fp32 (dy, add, dx stay bf16). */
 int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-    const void* add, void* dx, float* ws, int ws_rows, int rows, int D, tris_stream_t stream);
+    const void* add, void* dx, float* ws, int ws_rows, int rows, int D, int x_f32, tris_stream_t stream);
 /* softmax(q k^T / 8 [+ causal mask]) v per (sample, head), head dim 64 (nn.MultiheadAttention in model.py:366-386). */
 int tris_attn_fwd(const void* qkv, void* out, int n, int L, int heads, int causal, tris_stream_t stream);
 /* its backward (dq, dk, dv packed like qkv). */

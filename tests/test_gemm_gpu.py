@@ -46,6 +46,12 @@ def test_linear_fwd_epilogue(G):
     pre = x.float() @ w.float().t() + bias
     out = G.linear_fwd(x, w, bias, act=L.ACT_QUICKGELU, residual=res)
     assert rel(out, pre * torch.sigmoid(1.702 * pre) + res.float()) < 1e-2
+    # fp32 residual stream of the transformer towers: fp32 residual in, fp32 out, nothing rounded to bf16 in between
+    res32 = torch.randn(m, n, device="cuda") * 3
+    out = G.linear_fwd(x, w, bias, residual=res32)
+    assert out.dtype == torch.float32 and rel(out, pre + res32) < 2e-4
+    out = G.linear_fwd(x[:77], w[:520], bias[:520], residual=res32[:77, :520].contiguous())     # ragged tile edges
+    assert rel(out, pre[:77, :520] + res32[:77, :520]) < 2e-4
     stats = torch.full((148 * 2 * n,), 7.0, device="cuda")     # partial rows: every row is written by the kernel
     out = G.linear_fwd(x, w, bias, act=L.ACT_RELU)
     assert rel(out, F.relu(pre)) < 1e-2

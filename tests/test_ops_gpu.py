@@ -168,6 +168,18 @@ def test_layernorm(K, d):
     gr = torch.autograd.grad(ref, [xt, gt, bt], dy.float())
     assert rel(dx, gr[0] + add.float()) < 1e-2
     assert rel(dg, gr[1]) < 5e-3 and rel(db, gr[2]) < 5e-3
+    # fp32 rows (the residual stream of the transformer towers): fp32 in -> bf16 out, bf16 in -> fp32 out, fp32 x in backward
+    x32 = torch.randn(rows, d, device="cuda") + 0.2
+    y2, mean2, rstd2 = K.layernorm_fwd(x32, g, b)
+    ref2 = F.layer_norm(x32, (d,), g, b, 1e-5)
+    assert y2.dtype == torch.bfloat16 and rel(y2, ref2) < 1e-2
+    assert rel(mean2, x32.mean(-1)) < 1e-5
+    y3, _, _ = K.layernorm_fwd(x, g, b, out_dtype=torch.float32)
+    assert y3.dtype == torch.float32 and rel(y3, ref) < 1e-5
+    x32t = x32.clone().requires_grad_(True)
+    gr2 = torch.autograd.grad(F.layer_norm(x32t, (d,), g, b, 1e-5), x32t, dy.float())[0]
+    dx2 = K.layernorm_bwd(dy, x32, g, mean2, rstd2, add=add)
+    assert dx2.dtype == torch.bfloat16 and rel(dx2, gr2 + add.float()) < 1e-2
 
 
 @pytest.mark.parametrize("n,l,heads,causal", [(5, 20, 8, True), (3, 50, 12, False), (2, 40, 8, True)])
@@ -198,6 +210,10 @@ def test_embedding_gather_scatter_colsum(K):
     ref = E[ids.long()] + Pp[:l]
     assert rel(x, ref.reshape(n * l, d)) < 1e-2
     assert torch.equal(eot.long(), torch.arange(n, device="cuda") * l + ids.long().argmax(-1))
+    x32, _ = K.embed_fwd(ids, E, Pp, out_dtype=torch.float32)
+    assert torch.equal(x32, ref.reshape(n * l, d))
+    pick = torch.tensor([3, 0, 77, 5], device="cuda", dtype=torch.int32)
+    assert torch.equal(K.gather_rows(x32, pick), x32[pick.long()])
     dx = rnd(n * l, d, seed=1)
     dE, dP = torch.zeros_like(E), torch.zeros_like(Pp)
     K.embed_bwd(ids, dx, dE, dP)

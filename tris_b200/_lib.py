@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
         ("d_norm", C.c_void_p), ("in_gamma", C.c_void_p), ("in_beta", C.c_void_p), ("in_mean", C.c_void_p), ("in_invstd", C.c_void_p),
         ("in_add", C.c_void_p), ("in_eps", C.c_float), ("in_mix", C.c_float), ("in_relu", C.c_int32),
         ("conv_halo", C.c_int32),
-        ("res_bits", C.c_void_p), ("tstamp", C.c_void_p),
+        ("res_bits", C.c_void_p), ("tstamp", C.c_void_p), ("residual_f32", C.c_int32),
     ]
 
 

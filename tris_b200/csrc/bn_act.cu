@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32 * kFinGroups) bn_fwd_finalize_kernel(const 
     bn_fwd_finalize_group(p, blockIdx.y, blockIdx.x, sm);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyParams p) {
     extern __shared__ float sm[];
     float* sc0 = sm;
     float* sh0 = sm + p.c;
@@ -231,8 +231,10 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
         a0[i] = sc0[c0 + i]; b0[i] = sh0[c0 + i];
         a1[i] = dual ? sc1[c0 + i] : 0.f; b1[i] = dual ? sh1[c0 + i] : 0.f;
     }
+    const int unpair_j = c0 >= (p.c >> 1), unpair_c0 = c0 - unpair_j * (p.c >> 1);
     for (long orow = start / vecs; orow < rows_out; orow += row_step) {
         Vec8 acc;
+        __nv_bfloat16* dst = p.out + orow * p.c + c0;
         if (p.pool == 1) {
             acc = ld8(p.b0.y + orow * p.c + c0);
 #pragma unroll
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
             const long t = orow / wo;
             const int yo = static_cast<int>(t % ho);
             const long ni = t / ho;
+            if (p.unpair)         // (pair ni, channel half j) -> image 2 ni + j with c/2 channels
+                dst = p.out + (((2 * ni + unpair_j) * ho + yo) * wo + xo) * (p.c >> 1) + unpair_c0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
 #pragma unroll
@@ -272,14 +276,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParam
                     }
                 }
         }
-        if (p.unpair) {       // (pair ni, channel half j) -> image 2 ni + j with c/2 channels
-            const int half = p.c >> 1, j = c0 >= half;
-            const long hw = static_cast<long>(ho) * wo;
-            const long ni = orow / hw, rem = orow - ni * hw;
-            st8(p.out + ((2 * ni + j) * hw + rem) * half + (c0 - j * half), acc);
-        } else {
-            st8(p.out + orow * p.c + c0, acc);
-        }
+        st8(dst, acc);
         if (p.relu_bits != nullptr) {
             unsigned b = 0;
 #pragma unroll

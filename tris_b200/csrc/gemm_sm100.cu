@@ -84,7 +84,7 @@ struct KParams {
     unsigned long long* tstamp;      // optional [2]: min(%globaltimer at CTA start), max(%globaltimer at CTA end) of this launch
     __nv_bfloat16* d_pre;            // optional: pre-activation (post-bias) output, bf16 [M, ldd]
     const __nv_bfloat16* dact_src;   // optional: multiply by act'(dact_src[row, col]) instead of applying act
-    int ldd, act, out_f32, atomic;
+    int ldd, act, out_f32, atomic, res_f32;
     float scale;                     // accumulator scale applied before the bias (1 = none)
 };
 
@@ -552,7 +552,16 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                 }
                 auto add_residual = [&]() {
-                    if (p.residual != nullptr && rvalid) {
+                    if (p.residual != nullptr && rvalid && p.res_f32) {
+                        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            if (ncol0 + g * 4 < p.N) {
+                                const float4 f = __ldg(rp + g);
+                                v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+                            }
+                        }
+                    } else if (p.residual != nullptr && rvalid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
                         uint32_t bits = 0xffffffffu;
                         if (p.res_bits != nullptr) bits = __ldg(reinterpret_cast<const uint32_t*>(p.res_bits + grow * (p.N >> 3) + (ncol0 >> 3)));
@@ -1072,6 +1081,8 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.d_pre = reinterpret_cast<__nv_bfloat16*>(g->d_pre);
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;
+    p.res_f32 = g->residual_f32;
+    if (g->residual_f32 && (!g->residual || g->res_bits || g->N % 4)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: residual_f32 needs a residual, no res_bits, N %% 4 == 0");
     p.scale = g->scale == 0.f ? 1.f : g->scale;
 
     // ---- tensor maps

@@ -26,8 +26,9 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---------------------------------------------------------------------------------------- embedding
 // one block per sentence: x[n,l,:] = E[ids[n,l]] + P[l]; eot[n] = n*L + argmax_l ids[n,l] (first maximum)
+template <bool XF32>   // XF32: the residual stream starts in fp32 (as the reference's autocast keeps it)
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ E, const float* __restrict__ P,
-                                 __nv_bfloat16* __restrict__ x, int* __restrict__ eot, int L, int D) {
+                                 void* __restrict__ xv, int* __restrict__ eot, int L, int D) {
     const int n = blockIdx.x;
     if (threadIdx.x == 0 && eot != nullptr) {
         int best = 0, bv = ids[n * L];
@@ -42,9 +43,14 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __res
         const int tok = ids[n * L + l];
         const float4 e = __ldg(reinterpret_cast<const float4*>(E + static_cast<long>(tok) * D + d));
         const float4 p = __ldg(reinterpret_cast<const float4*>(P + l * D + d));
-        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(x + (static_cast<long>(n) * L + l) * D + d);
-        o[0] = __floats2bfloat162_rn(e.x + p.x, e.y + p.y);
-        o[1] = __floats2bfloat162_rn(e.z + p.z, e.w + p.w);
+        const long off = (static_cast<long>(n) * L + l) * D + d;
+        if (XF32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(xv) + off) = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+        } else {
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(xv) + off);
+            o[0] = __floats2bfloat162_rn(e.x + p.x, e.y + p.y);
+            o[1] = __floats2bfloat162_rn(e.z + p.z, e.w + p.w);
+        }
     }
 }
 
@@ -116,20 +122,37 @@ __device__ __forceinline__ V8 ldf8(const float* p) {
     return o;
 }
 
-template <int NV>   // vectors per lane = D / 256
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+// row vectors of the residual stream: bf16, or fp32 (F32) -- element offset `off`
+template <bool F32>
+__device__ __forceinline__ V8 ldx8(const void* base, long off) {
+    if (F32) return ldf8(reinterpret_cast<const float*>(base) + off);
+    return ldv8(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+}
+template <bool F32>
+__device__ __forceinline__ void stx8(void* base, long off, const V8& x) {
+    if (F32) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+        p[0] = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        p[1] = make_float4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    } else {
+        stv8(reinterpret_cast<__nv_bfloat16*>(base) + off, x);
+    }
+}
+
+template <int NV, bool XF32, bool YF32>   // vectors per lane = D / 256
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, void* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             int rows, int D, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const __nv_bfloat16* xr = x + static_cast<long>(row) * D;
+    const long rbase = static_cast<long>(row) * D;
     V8 v[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        v[i] = ldv8(xr + (i * 32 + lane) * 8);
+        v[i] = ldx8<XF32>(x, rbase + (i * 32 + lane) * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i].v[j];
     }
@@ -140,7 +163,6 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = v[i].v[j] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) / D + eps);
-    __nv_bfloat16* yr = y + static_cast<long>(row) * D;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 8;
@@ -148,14 +170,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
         V8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] = (v[i].v[j] - mean) * rstd * g.v[j] + b.v[j];
-        stv8(yr + c, o);
+        stx8<YF32>(y, rbase + c, o);
     }
     if (lane == 0 && mean_out != nullptr) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
 // dx = (add ? add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += dy*xhat ; dbeta += dy
-template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <int NV, bool XF32>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ add,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ ws,
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 8;
-            const V8 d = ldv8(dy + base + c), xv = ldv8(x + base + c);
+            const V8 d = ldv8(dy + base + c), xv = ldx8<XF32>(x, base + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 xh[i].v[j] = (xv.v[j] - mean) * rstd;
@@ -507,11 +529,30 @@ static bool use_fp32_attention() {
     return v == 1;
 }
 
+template <int NV>
+static void launch_ln_fwd(dim3 grid, int threads, cudaStream_t st, int x_f32, int y_f32, const void* x, const float* gamma,
+                          const float* beta, void* y, float* mean, float* rstd, int rows, int D, float eps) {
+    if (x_f32 && y_f32) layernorm_fwd_kernel<NV, true, true><<<grid, threads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps);
+    else if (x_f32) layernorm_fwd_kernel<NV, true, false><<<grid, threads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps);
+    else if (y_f32) layernorm_fwd_kernel<NV, false, true><<<grid, threads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps);
+    else layernorm_fwd_kernel<NV, false, false><<<grid, threads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps);
+}
+
+template <int NV>
+static void launch_ln_bwd(int grid, int threads, size_t smb, cudaStream_t st, int x_f32, const __nv_bfloat16* dy, const void* x,
+                          const float* gamma, const float* mean, const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx,
+                          float* ws, int rows, int D) {
+    if (x_f32) layernorm_bwd_kernel<NV, true><<<grid, threads, smb, st>>>(dy, x, gamma, mean, rstd, add, dx, ws, rows, D);
+    else layernorm_bwd_kernel<NV, false><<<grid, threads, smb, st>>>(dy, x, gamma, mean, rstd, add, dx, ws, rows, D);
+}
+
 extern "C" {
 
-int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D, tris_stream_t stream) {
+int tris_embed_fwd(const int* ids, const float* E, const float* P, void* x, int* eot, int n, int L, int D, int x_f32,
+                   tris_stream_t stream) {
     if (D % 4) return tris::fail(TRIS_ERR_SHAPE, "tris_embed_fwd: D %% 4");
-    embed_fwd_kernel<<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, E, P, reinterpret_cast<__nv_bfloat16*>(x), eot, L, D);
+    if (x_f32) embed_fwd_kernel<true><<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, E, P, x, eot, L, D);
+    else embed_fwd_kernel<false><<<n, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, E, P, x, eot, L, D);
     TRIS_LAUNCH_OK("embed_fwd_kernel");
     return TRIS_OK;
 }
@@ -529,25 +570,23 @@ int tris_embed_bwd(const int* ids, const void* dx, float* dE, float* dP, int n, 
 }
 
 int tris_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int rows, int D,
-                       float eps, tris_stream_t stream) {
+                       float eps, int x_f32, int y_f32, tris_stream_t stream) {
     if (D % 256 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_fwd: D=%d must be a multiple of 256, <= 1024", D);
     const int warps = 8;
     const dim3 grid((rows + warps - 1) / warps);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
-    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
     switch (D / 256) {
-        case 1: layernorm_fwd_kernel<1><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
-        case 2: layernorm_fwd_kernel<2><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
-        case 3: layernorm_fwd_kernel<3><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
-        default: layernorm_fwd_kernel<4><<<grid, warps * 32, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, D, eps); break;
+        case 1: launch_ln_fwd<1>(grid, warps * 32, st, x_f32, y_f32, x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+        case 2: launch_ln_fwd<2>(grid, warps * 32, st, x_f32, y_f32, x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+        case 3: launch_ln_fwd<3>(grid, warps * 32, st, x_f32, y_f32, x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+        default: launch_ln_fwd<4>(grid, warps * 32, st, x_f32, y_f32, x, gamma, beta, y, mean, rstd, rows, D, eps); break;
     }
     TRIS_LAUNCH_OK("layernorm_fwd_kernel");
     return TRIS_OK;
 }
 
 int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* add,
-                       void* dx, float* ws, int ws_rows, int rows, int D, tris_stream_t stream) {
+                       void* dx, float* ws, int ws_rows, int rows, int D, int x_f32, tris_stream_t stream) {
     if (D % 256 || D > 1024) return tris::fail(TRIS_ERR_SHAPE, "tris_layernorm_bwd: D=%d must be a multiple of 256, <= 1024", D);
     const int warps = 8;
     int grid = (rows + warps - 1) / warps;
@@ -559,15 +598,14 @@ int tris_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
         grid = 4 * tris::sm_count();
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16*>(dy), *xp = reinterpret_cast<const __nv_bfloat16*>(x),
-                        *ap = reinterpret_cast<const __nv_bfloat16*>(add);
+    const __nv_bfloat16 *dyp = reinterpret_cast<const __nv_bfloat16*>(dy), *ap = reinterpret_cast<const __nv_bfloat16*>(add);
     __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
     const size_t smb = 2 * D * sizeof(float);
     switch (D / 256) {
-        case 1: layernorm_bwd_kernel<1><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
-        case 2: layernorm_bwd_kernel<2><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
-        case 3: layernorm_bwd_kernel<3><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
-        default: layernorm_bwd_kernel<4><<<grid, warps * 32, smb, st>>>(dyp, xp, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        case 1: launch_ln_bwd<1>(grid, warps * 32, smb, st, x_f32, dyp, x, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        case 2: launch_ln_bwd<2>(grid, warps * 32, smb, st, x_f32, dyp, x, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        case 3: launch_ln_bwd<3>(grid, warps * 32, smb, st, x_f32, dyp, x, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
+        default: launch_ln_bwd<4>(grid, warps * 32, smb, st, x_f32, dyp, x, gamma, mean, rstd, ap, dxp, ws, rows, D); break;
     }
     TRIS_LAUNCH_OK("layernorm_bwd_kernel");
     return TRIS_OK;

@@ -160,15 +160,18 @@ def linear_fwd(x, w, bias=None, act=L.ACT_NONE, residual=None, out=None, out_dty
     m, k = x.shape
     n = w.shape[0]
     assert w.shape[1] == k
+    res_f32 = residual is not None and residual.dtype == torch.float32     # fp32 residual stream: fp32 in, fp32 out
     if out is None:
-        out = torch.empty((m, n), device=x.device, dtype=out_dtype)
+        out = torch.empty((m, n), device=x.device, dtype=torch.float32 if res_f32 else out_dtype)
+    assert not res_f32 or out.dtype == torch.float32
     tiles_m = (m + 127) // 128
     bn = block_n or _bn_for(n, tiles_m, k=k)
     if out.dtype == torch.float32:
         bn = min(bn, 128)
     d = _desc(a=L.ptr(x), b=L.ptr(w), d=L.ptr(out), bias=L.ptr(bias), residual=L.ptr(residual), stats=L.ptr(stats),
               a_mode=L.OP_K2D, b_mode=L.OP_K2D, M=m, N=n, K=k, lda=k, ldb=k, ldd=n, taps=1, block_n=bn, split_k=1,
-              act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16, d_pre=L.ptr(d_pre))
+              act=act, out_dtype=L.DT_F32 if out.dtype == torch.float32 else L.DT_BF16, d_pre=L.ptr(d_pre),
+              residual_f32=int(res_f32))
     L.gemm_raw(d)
     return out
 

@@ -97,12 +97,12 @@ def avgpool2_bwd(dout, add=None):
 
 
 # ------------------------------------------------------------------ transformer pieces
-def embed_fwd(ids, E, Ppos, want_eot=True):
+def embed_fwd(ids, E, Ppos, want_eot=True, out_dtype=bf16):
     n, l = ids.shape
     d = E.shape[1]
-    x = torch.empty((n * l, d), device=E.device, dtype=bf16)
+    x = torch.empty((n * l, d), device=E.device, dtype=out_dtype)
     eot = torch.empty((n,), device=E.device, dtype=torch.int32) if want_eot else None
-    L.call("tris_embed_fwd", _vp(ids), _vp(E), _vp(Ppos), _vp(x), _vp(eot), n, l, d)
+    L.call("tris_embed_fwd", _vp(ids), _vp(E), _vp(Ppos), _vp(x), _vp(eot), n, l, d, int(out_dtype == f32))
     return x, eot
 
 
@@ -111,12 +111,14 @@ def embed_bwd(ids, dx, dE, dP):
     L.call("tris_embed_bwd", _vp(ids), _vp(dx), _vp(dE), _vp(dP), n, l, dE.shape[1])
 
 
-def layernorm_fwd(x, gamma, beta, save=True, eps=1e-5):
+def layernorm_fwd(x, gamma, beta, save=True, eps=1e-5, out_dtype=bf16):
+    """x: bf16 or fp32 rows (the fp32 residual stream of the transformer towers); y: out_dtype."""
     rows, d = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty((rows, d), device=x.device, dtype=out_dtype)
     mean = torch.empty((rows,), device=x.device, dtype=f32) if save else None
     rstd = torch.empty((rows,), device=x.device, dtype=f32) if save else None
-    L.call("tris_layernorm_fwd", _vp(x), _vp(gamma), _vp(beta), _vp(y), _vp(mean), _vp(rstd), rows, d, C.c_float(eps))
+    L.call("tris_layernorm_fwd", _vp(x), _vp(gamma), _vp(beta), _vp(y), _vp(mean), _vp(rstd), rows, d, C.c_float(eps),
+           int(x.dtype == f32), int(out_dtype == f32))
     return y, mean, rstd
 
 
@@ -131,12 +133,13 @@ def _queue(queue):
 def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, queue=None):
     """dgamma / dbeta (fp32 [D], accumulated): per-CTA partial rows + an in-order sum through the queue (no atomics)."""
     rows, d = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty((rows, d), device=x.device, dtype=bf16)      # the gradient stream is bf16 whatever the dtype of x
     ws, nrows = None, 0
     if dgamma is not None:
         nrows = max(1, min((rows + 7) // 8, 148))
         ws = torch.empty((2, nrows, d), device=x.device, dtype=f32)
-    L.call("tris_layernorm_bwd", _vp(dy), _vp(x), _vp(gamma), _vp(mean), _vp(rstd), _vp(add), _vp(dx), _vp(ws), nrows, rows, d)
+    L.call("tris_layernorm_bwd", _vp(dy), _vp(x), _vp(gamma), _vp(mean), _vp(rstd), _vp(add), _vp(dx), _vp(ws), nrows, rows, d,
+           int(x.dtype == f32))
     if ws is not None:
         q, now = _queue(queue)
         q.push(ws[0], dgamma, 1, d, d, nrows, True)
@@ -159,6 +162,9 @@ def attn_bwd(qkv, dout, n, l, heads, causal):
 
 
 def gather_rows(x, idx):
+    """Rows of a bf16 or fp32 matrix (fp32 rows are copied as pairs of 16-bit words by the same kernel)."""
+    if x.dtype == f32:
+        return gather_rows(x.view(bf16), idx).view(f32)
     out = torch.empty((idx.numel(), x.shape[1]), device=x.device, dtype=bf16)
     L.call("tris_gather_rows", _vp(x), _vp(idx), _vp(out), idx.numel(), x.shape[1])
     return out

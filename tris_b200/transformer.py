@@ -9,6 +9,8 @@ Activations bf16, statistics fp32.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -16,6 +18,12 @@ from . import gemm as G
 from . import ops
 
 bf16, f32 = torch.bfloat16, torch.float32
+
+# The residual stream between transformer blocks is kept in fp32 (forward values; gradients stay bf16): under torch.autocast the
+# reference does the same -- fp32 embeddings + bf16 branch outputs promote to fp32 (CLIP/clip/model.py:383-386) -- and the tensors
+# are small ([960, 512] / [2400, 768]).  Measured: the bf16 stream put 1.0 % noise on the sentence features, which moved the
+# classification loss by up to -0.8 % (profiles/r2_loss_bias_split.txt).  TRIS_RESIDUAL_F32=0 restores the bf16 stream.
+STREAM_DTYPE = f32 if os.environ.get("TRIS_RESIDUAL_F32", "1") != "0" else bf16
 
 
 class TransformerStack:
@@ -83,7 +91,7 @@ class TextTower:
         st, p = self.st, self.prefix
         n, l = ids.shape
         ids = ids.to(torch.int32).contiguous()
-        x0, eot = ops.embed_fwd(ids, st.p(p + "token_embedding.weight"), st.p(p + "positional_embedding"))
+        x0, eot = ops.embed_fwd(ids, st.p(p + "token_embedding.weight"), st.p(p + "positional_embedding"), out_dtype=STREAM_DTYPE)
         x, tape = self.stack.forward(x0, n, l, save)
         xe = ops.gather_rows(x, eot)
         xn, m, r = ops.layernorm_fwd(xe, st.p(p + "ln_final.weight"), st.p(p + "ln_final.bias"), save)
@@ -130,7 +138,7 @@ class VitTower:
         w = st.s(p + "conv1.weight")
         pe = G.linear_fwd(patches, w.view(w.shape[0], -1))
         tok = ops.vit_assemble(pe, st.p(p + "class_embedding"), st.p(p + "positional_embedding"), n)
-        x0, m0, r0 = ops.layernorm_fwd(tok, st.p(p + "ln_pre.weight"), st.p(p + "ln_pre.bias"), save)
+        x0, m0, r0 = ops.layernorm_fwd(tok, st.p(p + "ln_pre.weight"), st.p(p + "ln_pre.bias"), save, out_dtype=STREAM_DTYPE)
         x, tape = self.stack.forward(x0, n, self.tokens, save)
         cls_idx, patch_idx = self._idx(n, patches.device)
         xc = ops.gather_rows(x, cls_idx)
