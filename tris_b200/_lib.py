@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtris_sm100.so")
+LIB_PATH = os.environ.get("TRIS_LIB_PATH") or os.path.join(_HERE, "lib", "libtris_sm100.so")   # override: A/B builds of the same ABI
 
 OP_K2D, OP_MN2D, OP_CONV = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_QUICKGELU = 0, 1, 2

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(32 * kFinGroups) bn_fwd_finalize_kernel(const 
     bn_fwd_finalize_group(p, blockIdx.y, blockIdx.x, sm);
 }
 
-__global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyParams p) {
+template <bool UNPAIR>
+__device__ __forceinline__ void bn_apply_fwd_body(const ApplyParams& p) {
     extern __shared__ float sm[];
     float* sc0 = sm;
     float* sh0 = sm + p.c;
@@ -231,10 +232,9 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyPa
         a0[i] = sc0[c0 + i]; b0[i] = sh0[c0 + i];
         a1[i] = dual ? sc1[c0 + i] : 0.f; b1[i] = dual ? sh1[c0 + i] : 0.f;
     }
-    const int unpair_j = c0 >= (p.c >> 1), unpair_c0 = c0 - unpair_j * (p.c >> 1);
     for (long orow = start / vecs; orow < rows_out; orow += row_step) {
         Vec8 acc;
-        __nv_bfloat16* dst = p.out + orow * p.c + c0;
+        long urow = 0;        // UNPAIR: output row in the un-paired layout
         if (p.pool == 1) {
             acc = ld8(p.b0.y + orow * p.c + c0);
 #pragma unroll
@@ -258,8 +258,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyPa
             const long t = orow / wo;
             const int yo = static_cast<int>(t % ho);
             const long ni = t / ho;
-            if (p.unpair)         // (pair ni, channel half j) -> image 2 ni + j with c/2 channels
-                dst = p.out + (((2 * ni + unpair_j) * ho + yo) * wo + xo) * (p.c >> 1) + unpair_c0;
+            if (UNPAIR) urow = ((2 * ni + (c0 >= (p.c >> 1))) * ho + yo) * wo + xo;   // (pair ni, half j) -> image 2 ni + j
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
 #pragma unroll
@@ -276,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyPa
                     }
                 }
         }
-        st8(dst, acc);
+        if (UNPAIR) st8(p.out + urow * (p.c >> 1) + (c0 >= (p.c >> 1) ? c0 - (p.c >> 1) : c0), acc);
+        else st8(p.out + orow * p.c + c0, acc);
         if (p.relu_bits != nullptr) {
             unsigned b = 0;
 #pragma unroll
@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_kernel(const ApplyPa
         }
     }
 }
+
+__global__ void __launch_bounds__(kThreads) bn_apply_fwd_kernel(const ApplyParams p) { bn_apply_fwd_body<false>(p); }
+// pair-packed stem: un-paired output addressing (a few more registers: capped so that 4 CTAs/SM stay resident)
+__global__ void __launch_bounds__(kThreads, 4) bn_apply_fwd_unpair_kernel(const ApplyParams p) { bn_apply_fwd_body<true>(p); }
 
 // ------------------------------------------------------------------------------------------------ backward
 struct BwdParams {
@@ -314,9 +318,10 @@ __device__ __forceinline__ Vec8 lds8(const float* s) {
 
 // g at output row orow for channel group c0, masked (ReLU) and pool-scaled.  sc/sh: smem scale/shift of branch 0 (mask
 // recompute when the forward output was not kept).
+template <bool UNPAIR>
 __device__ __forceinline__ Vec8 masked_grad(const BwdParams& p, long orow, int c0, const Vec8& y0, const float* s_sc, const float* s_sh) {
     Vec8 g;
-    if (p.unpair) {
+    if (UNPAIR) {
         const int half = p.c >> 1, j = c0 >= half;
         const long hw = static_cast<long>(p.h / 2) * (p.w / 2);
         const long ni = orow / hw, rem = orow - ni * hw;
@@ -356,7 +361,7 @@ __device__ __forceinline__ long out_row_of(const BwdParams& p, long irow) {
 }
 
 // dbeta = sum g ; dgamma = invstd * sum g (y - mean).   smem: sc0 [C], sh0 [C], mu0 [C], mu1 [C], then the reduction scratch.
-template <bool DUAL>
+template <bool DUAL, bool UNPAIR>
 __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdParams p) {
     extern __shared__ float sm[];
     float* s_sc = sm;
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const BwdPar
         const Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
         Vec8 y1;
         if (DUAL) y1 = ld8(p.b1.y + irow * p.c + c0);
-        const Vec8 g = masked_grad(p, orow, c0, y0, s_sc, s_sh);
+        const Vec8 g = masked_grad<UNPAIR>(p, orow, c0, y0, s_sc, s_sh);
         const Vec8 mu0 = lds8(s_mu0 + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(32 * kFinGroupsBwd) bn_bwd_finalize_kernel(con
 
 // dy = a g + b y + c per channel with  a = gamma*invstd,  b = -a*invstd*dgamma/N,  c = a*(invstd*dgamma/N*mean - dbeta/N).
 // smem: sc0, sh0, b0, c0, (dual) a1, b1, c1  -- each [C].
-template <bool DUAL>
+template <bool DUAL, bool UNPAIR>
 __global__ void __launch_bounds__(kThreads, 4) bn_bwd_apply_kernel(const BwdParams p) {
     extern __shared__ float sm[];
     float* s_sc = sm;
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_apply_kernel(const BwdPara
         const Vec8 y0 = ld8(p.b0.y + irow * p.c + c0);
         Vec8 y1;
         if (DUAL) y1 = ld8(p.b1.y + irow * p.c + c0);
-        const Vec8 g = masked_grad(p, orow, c0, y0, s_sc, s_sh);
+        const Vec8 g = masked_grad<UNPAIR>(p, orow, c0, y0, s_sc, s_sh);
         Vec8 d;
         {
             const Vec8 a = lds8(s_sc + c0), b = lds8(s_b0 + c0), c = lds8(s_c0 + c0);
@@ -621,9 +626,11 @@ int tris_bn_apply_fwd(const void* y0, const float* stats0, const float* gamma0, 
     }
     const long total = static_cast<long>(n) * (h / pool) * (w / pool) * (c / 8);
     if (train) {
-        TRIS_CUDA_OK(launch_dep(bn_apply_fwd_kernel, dim3(grid_for(total)), dim3(kThreads), 4 * c * sizeof(float), s, p));
+        if (unpair) TRIS_CUDA_OK(launch_dep(bn_apply_fwd_unpair_kernel, dim3(grid_for(total)), dim3(kThreads), 4 * c * sizeof(float), s, p));
+        else TRIS_CUDA_OK(launch_dep(bn_apply_fwd_kernel, dim3(grid_for(total)), dim3(kThreads), 4 * c * sizeof(float), s, p));
     } else {
-        bn_apply_fwd_kernel<<<grid_for(total), kThreads, 4 * c * sizeof(float), s>>>(p);
+        if (unpair) bn_apply_fwd_unpair_kernel<<<grid_for(total), kThreads, 4 * c * sizeof(float), s>>>(p);
+        else bn_apply_fwd_kernel<<<grid_for(total), kThreads, 4 * c * sizeof(float), s>>>(p);
         TRIS_LAUNCH_OK("bn_apply_fwd_kernel");
     }
     return TRIS_OK;
@@ -658,7 +665,7 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     p.dy0 = reinterpret_cast<__nv_bfloat16*>(dy0);
     p.dy1 = reinterpret_cast<__nv_bfloat16*>(dy1);
     p.g_out = reinterpret_cast<__nv_bfloat16*>(g_out);
-    if (unpair && (pool != 2 || c % 16)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: unpair needs pool 2, c %% 16 == 0");
+    if (unpair && (pool != 2 || c % 16 || y1)) return tris::fail(TRIS_ERR_SHAPE, "tris_bn_bwd: unpair needs pool 2, c %% 16 == 0, one branch");
     p.n = n; p.h = h; p.w = w; p.c = c; p.pool = pool; p.relu = ext_parts > 0 ? 0 : relu; p.unpair = unpair;
     p.count = static_cast<float>(static_cast<long>(n) * h * w);
     p.kred = y1 ? 3 : 2;
@@ -678,18 +685,21 @@ int tris_bn_bwd(const void* dout, const void* out, const void* y0, const float* 
     const size_t rsmem = (4 * c + kThreads * 8) * sizeof(float), asmem = 7 * c * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
-        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
+        TRIS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_apply_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4));
         attr = true;
     }
     if (ext_parts == 0) {
-        if (y1 != nullptr) bn_bwd_reduce_kernel<true><<<rgrid, kThreads, rsmem, s>>>(p);
-        else bn_bwd_reduce_kernel<false><<<rgrid, kThreads, rsmem, s>>>(p);
+        if (y1 != nullptr) bn_bwd_reduce_kernel<true, false><<<rgrid, kThreads, rsmem, s>>>(p);
+        else if (unpair) bn_bwd_reduce_kernel<false, true><<<rgrid, kThreads, rsmem, s>>>(p);
+        else bn_bwd_reduce_kernel<false, false><<<rgrid, kThreads, rsmem, s>>>(p);
         TRIS_LAUNCH_OK("bn_bwd_reduce_kernel");
     }
     TRIS_CUDA_OK(launch_dep(bn_bwd_finalize_kernel, dim3((c + 31) / 32), dim3(32 * kFinGroupsBwd), 0, s, p));
-    if (y1 != nullptr) TRIS_CUDA_OK(launch_dep(bn_bwd_apply_kernel<true>, dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
-    else TRIS_CUDA_OK(launch_dep(bn_bwd_apply_kernel<false>, dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
+    if (y1 != nullptr) TRIS_CUDA_OK(launch_dep((bn_bwd_apply_kernel<true, false>), dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
+    else if (unpair) TRIS_CUDA_OK(launch_dep((bn_bwd_apply_kernel<false, true>), dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
+    else TRIS_CUDA_OK(launch_dep((bn_bwd_apply_kernel<false, false>), dim3(grid_for(total)), dim3(kThreads), asmem, s, p));
     return TRIS_OK;
 }
 

@@ -144,6 +144,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // Loader variants (compile-time, so the single-thread producer / issuer loops carry no mode branches or divisions)
 enum { LD_K2D = 0, LD_MN2D = 1, LD_CONV = 2, LD_CONV_WG = 3, LD_MN2D_TAPS = 4, LD_CONV_HALO = 5 };
 
+// EPI = 3: the residual is fp32 (residual stream of the transformer towers).
 // EPI = 1 adds the BatchNorm-backward epilogue (recomputed ReLU mask from y, sums (g, g (y - mu))): compiled separately so
 // that the common kernels do not carry its code.
 template <int AM, int BM, int EPI>
@@ -552,7 +553,8 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                 }
                 auto add_residual = [&]() {
-                    if (p.residual != nullptr && rvalid && p.res_f32) {
+                    if (EPI == 3) {      // fp32 residual (instantiated separately: the hot instantiations keep their code)
+                      if (p.residual != nullptr && rvalid) {
                         const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off);
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
@@ -561,6 +563,7 @@ tris_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                 v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
                             }
                         }
+                      }
                     } else if (p.residual != nullptr && rvalid) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
                         uint32_t bits = 0xffffffffu;
@@ -1082,7 +1085,9 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     p.dact_src = reinterpret_cast<const __nv_bfloat16*>(g->dact_src);
     p.ldd = g->ldd; p.act = g->act; p.out_f32 = g->out_dtype == TRIS_DT_F32; p.atomic = g->atomic;
     p.res_f32 = g->residual_f32;
-    if (g->residual_f32 && (!g->residual || g->res_bits || g->N % 4)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: residual_f32 needs a residual, no res_bits, N %% 4 == 0");
+    if (g->residual_f32 && (!g->residual || g->res_bits || g->N % 4 || g->a_mode != TRIS_OP_K2D || g->b_mode != TRIS_OP_K2D || batch > 1 ||
+                            g->stats || g->dact_src))
+        return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: residual_f32 needs a residual, plain K-major 2-D operands, no res_bits / stats / dact, N %% 4 == 0");
     p.scale = g->scale == 0.f ? 1.f : g->scale;
 
     // ---- tensor maps
@@ -1183,7 +1188,8 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     KernelFn fn = nullptr;
     const int epi = inorm ? 2 : ((g->stats_mode == 1 || g->mask_sc != nullptr) ? 1 : 0);
 #define TRIS_PICK(A_, B_) (epi == 1 ? static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 1>) : static_cast<KernelFn>(tris_umma_gemm_kernel<A_, B_, 0>))
-    if (am == LD_K2D && bm == LD_K2D) fn = epi == 2 ? static_cast<KernelFn>(tris_umma_gemm_kernel<LD_K2D, LD_K2D, 2>) : TRIS_PICK(LD_K2D, LD_K2D);
+    if (am == LD_K2D && bm == LD_K2D && g->residual_f32) fn = tris_umma_gemm_kernel<LD_K2D, LD_K2D, 3>;
+    else if (am == LD_K2D && bm == LD_K2D) fn = epi == 2 ? static_cast<KernelFn>(tris_umma_gemm_kernel<LD_K2D, LD_K2D, 2>) : TRIS_PICK(LD_K2D, LD_K2D);
     else if (am == LD_K2D && bm == LD_MN2D) fn = TRIS_PICK(LD_K2D, LD_MN2D);
     else if (am == LD_MN2D && bm == LD_MN2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_MN2D, 0>;
     else if (am == LD_MN2D && bm == LD_K2D) fn = tris_umma_gemm_kernel<LD_MN2D, LD_K2D, 0>;

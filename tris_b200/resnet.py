@@ -102,7 +102,7 @@ class ResNetTower:
         from .engine import OVERLAP
         st, p = self.store, self.prefix
         main = torch.cuda.current_stream()
-        if OVERLAP:
+        if OVERLAP and os.environ.get("TRIS_PACK_SIDE", "1") != "0":
             if self._pack_stream is None:
                 self._pack_stream = torch.cuda.Stream()
             side = self._pack_stream

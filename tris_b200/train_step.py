@@ -145,13 +145,18 @@ class Stage1Trainer:
         self.model.train()
         # clearing the 454 MB flat gradient buffer (61 us) runs next to the forward pass; joined in front of the backward pass
         main = torch.cuda.current_stream()
-        if self._zero_stream is None:
-            self._zero_stream = torch.cuda.Stream()
-        self._zero_stream.wait_stream(main)
-        with torch.cuda.stream(self._zero_stream):
+        side_zero = os.environ.get("TRIS_ZERO_SIDE", "1") != "0"
+        if side_zero:
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream()
+            self._zero_stream.wait_stream(main)
+            with torch.cuda.stream(self._zero_stream):
+                self.eng.store.zero_grad()
+        else:
             self.eng.store.zero_grad()
         losses = stage1_losses(self.model, self.aux, img, word_ids, neg_word_ids, *self.w)
-        main.wait_stream(self._zero_stream)
+        if side_zero:
+            main.wait_stream(self._zero_stream)
         losses["loss"].backward()
         return losses
 

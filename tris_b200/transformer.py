@@ -23,7 +23,10 @@ bf16, f32 = torch.bfloat16, torch.float32
 # reference does the same -- fp32 embeddings + bf16 branch outputs promote to fp32 (CLIP/clip/model.py:383-386) -- and the tensors
 # are small ([960, 512] / [2400, 768]).  Measured: the bf16 stream put 1.0 % noise on the sentence features, which moved the
 # classification loss by up to -0.8 % (profiles/r2_loss_bias_split.txt).  TRIS_RESIDUAL_F32=0 restores the bf16 stream.
+# The frozen ViT-B/32 (on the critical path of the step; its features only enter the two small CLIP-guided terms, which deviate
+# by < 0.1 % either way) keeps the bf16 stream unless TRIS_VIT_RESIDUAL_F32=1.
 STREAM_DTYPE = f32 if os.environ.get("TRIS_RESIDUAL_F32", "1") != "0" else bf16
+VIT_STREAM_DTYPE = f32 if os.environ.get("TRIS_VIT_RESIDUAL_F32", "0") == "1" else bf16
 
 
 class TransformerStack:
@@ -138,7 +141,7 @@ class VitTower:
         w = st.s(p + "conv1.weight")
         pe = G.linear_fwd(patches, w.view(w.shape[0], -1))
         tok = ops.vit_assemble(pe, st.p(p + "class_embedding"), st.p(p + "positional_embedding"), n)
-        x0, m0, r0 = ops.layernorm_fwd(tok, st.p(p + "ln_pre.weight"), st.p(p + "ln_pre.bias"), save, out_dtype=STREAM_DTYPE)
+        x0, m0, r0 = ops.layernorm_fwd(tok, st.p(p + "ln_pre.weight"), st.p(p + "ln_pre.bias"), save, out_dtype=VIT_STREAM_DTYPE)
         x, tape = self.stack.forward(x0, n, self.tokens, save)
         cls_idx, patch_idx = self._idx(n, patches.device)
         xc = ops.gather_rows(x, cls_idx)
