@@ -1201,10 +1201,11 @@ extern "C" int tris_gemm(tris_gemm_desc* g, tris_stream_t stream_) {
     else return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: unsupported operand mode combination a=%d b=%d", g->a_mode, g->b_mode);
 #undef TRIS_PICK
     if (epi && (am == LD_MN2D || am == LD_CONV_WG)) return tris::fail(TRIS_ERR_SHAPE, "tris_gemm: BatchNorm-backward epilogue needs a K-major / conv A operand");
-    static bool attr_set[8][8][3] = {};
-    if (!attr_set[am][bm][epi]) {
+    static bool attr_set[8][8][4] = {};
+    const int inst = g->residual_f32 ? 3 : epi;
+    if (!attr_set[am][bm][inst]) {
         TRIS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[am][bm][epi] = true;
+        attr_set[am][bm][inst] = true;
     }
     const int total_tiles = p.tiles_tap * p.tiles_m * p.tiles_n * p.split_k * p.batch;
     int ctas = tris::sm_count();
