@@ -49,6 +49,7 @@ def main(args):
     from tris_b200 import ops
     from tris_b200.model_stage1 import TRIS
     img, ids, (h, w) = prepare(args)
+    torch.manual_seed(0)          # --synthetic-weights: the same random initialisation on every run
     model = TRIS(args).cuda().set_precision(args.precision).eval()
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
@@ -56,10 +57,12 @@ def main(args):
     with torch.no_grad():
         out = model(img.cuda(), ids.cuda())                                  # [1,1,S,S]
         cam = ops.resize_bilinear_ac(out, h, w)[0, 0]
+    raw = (cam.min().item(), cam.max().item())
     cam = (cam - cam.min()) / (cam.max() - cam.min() + 1e-5)
     path = args.output or "demo_cam.npy"
     np.save(path, cam.cpu().numpy())
-    print(f"response map {tuple(cam.shape)} min {cam.min().item():.3f} max {cam.max().item():.3f} -> {path}")
+    print(f"response map {tuple(cam.shape)} raw range [{raw[0]:.4f}, {raw[1]:.4f}] -> min-max normalised "
+          f"[{cam.min().item():.3f}, {cam.max().item():.3f}] -> {path}")
 
 
 if __name__ == "__main__":
