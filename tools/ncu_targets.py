@@ -20,6 +20,15 @@ oc = torch.empty_like(xc); stc = torch.zeros(148 * 256, device="cuda"); gwc = to
 targets.append(lambda: G.conv3x3_fwd(xc, wc, stats=stc, out=oc))
 targets.append(lambda: G.conv3x3_dgrad(dyc, wc, 128, out=oc))
 targets.append(lambda: G.conv3x3_wgrad(dyc, xc, out=gwc))
+# layer1 3x3 conv (halo re-use, weight-stationary) forward / dgrad / wgrad  48x80x80x64
+xh, wh, dyh = rnd(48, 80, 80, 64), rnd(64, 9 * 64), rnd(48, 80, 80, 64)
+oh = torch.empty_like(xh); sth = torch.zeros(148 * 128, device="cuda"); gwh = torch.zeros(64, 9 * 64, device="cuda")
+targets.append(lambda: G.conv3x3_fwd(xh, wh, stats=sth, out=oh))
+targets.append(lambda: G.conv3x3_dgrad(dyh, wh, 64, out=oh))
+targets.append(lambda: G.conv3x3_wgrad(dyh, xh, out=gwh))
+# layer1 1x1 conv 64 -> 256 + BN statistics (K = 64: HBM-bound, two-group epilogue)  [307200,64] x [256,64]^T
+x3, w3 = rnd(307200, 64), rnd(256, 64); o3 = torch.empty(307200, 256, device="cuda", dtype=bf16); st3 = torch.zeros(148 * 512, device="cuda")
+targets.append(lambda: G.linear_fwd(x3, w3, out=o3, stats=st3))
 # BatchNorm backward on the largest bottleneck tensor  48x80x80x256
 y = rnd(48, 80, 80, 256); dout = rnd(48, 80, 80, 256); outf = torch.relu(y)
 mk = lambda: torch.rand(256, device="cuda") + 0.5
