@@ -889,12 +889,19 @@ extern "C" int tris_splitk_reduce_multi(const tris_reduce_item* items, int n, tr
     for (int o = 0; o < n; o += TRIS_REDUCE_MAX) {
         ReduceTable t{};
         const int cnt = n - o < TRIS_REDUCE_MAX ? n - o : TRIS_REDUCE_MAX;
+        long max4 = 0;
         for (int i = 0; i < cnt; ++i) {
             t.it[i] = items[o + i];
             if (!t.it[i].ws || !t.it[i].d || t.it[i].w % 4 || t.it[i].ldd % 4 || t.it[i].rows <= 0 || t.it[i].split < 1)
                 return tris::fail(TRIS_ERR_SHAPE, "tris_splitk_reduce_multi: item %d malformed", o + i);
+            const long n4 = static_cast<long>(t.it[i].rows) * t.it[i].w / 4;
+            if (n4 > max4) max4 = n4;
         }
-        splitk_reduce_multi_kernel<<<dim3(32, cnt), 256, 0, stream>>>(t);
+        // CTAs per item sized for the largest item (4 output vectors per thread); the CTAs of small items exit at once.
+        // (32 CTAs per item left a 1024 x 1024 weight gradient to 8192 threads: 0.6 TB/s.)
+        long gx = (max4 + 1023) / 1024;
+        gx = gx < 32 ? 32 : (gx > 512 ? 512 : gx);
+        splitk_reduce_multi_kernel<<<dim3(static_cast<unsigned>(gx), cnt), 256, 0, stream>>>(t);
         TRIS_LAUNCH_OK("splitk_reduce_multi_kernel");
     }
     return TRIS_OK;
