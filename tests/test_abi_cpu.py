@@ -51,6 +51,31 @@ def test_library_is_sm100a_only(lib_path):
     assert archs == {"100a"}, archs
 
 
+def test_streaming_kernels_fit_one_resident_wave(lib_path):
+    """The BatchNorm streaming kernels are launched as ONE resident wave of 4 CTAs/SM x 256 threads: that only holds at <= 64
+    registers per thread (a 74-register build of bn_apply_fwd ran 3 CTAs/SM and cost 0.4 ms per step), and the GEMM
+    kernel is capped at 96 registers (352 threads + 214 KB of shared memory per SM).  Checked on the cubin, no GPU needed."""
+    import re
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", lib_path], capture_output=True, text=True).stdout
+    regs = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        regs[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    assert regs, "no resource usage parsed"
+    seen = 0
+    for name, (r, stack) in regs.items():
+        if re.search(r"bn_apply_fwd(_unpair)?_kernel|bn_bwd_reduce_kernel|bn_bwd_apply_kernel", name):
+            seen += 1
+            assert r <= 64, (name, r)
+        if "tris_umma_gemm_kernel" in name:
+            assert r <= 96 and stack <= 32, (name, r, stack)
+    assert seen >= 6
+
+
 def test_product_fails_loudly_without_device():
     import torch
     if torch.cuda.is_available():
