@@ -123,6 +123,7 @@ def main(args):
     torch.cuda.set_device(local)
     if not args.synthetic:
         raise SystemExit("validate.py: RefCOCO loaders are out of scope of this build (no dataset offline); use --synthetic")
+    torch.manual_seed(0)          # --synthetic-weights: the same random initialisation on every run
     model = TRIS(args).cuda().set_precision(args.precision)
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
