@@ -48,6 +48,8 @@ def get_parser():
                         "path offline); without it a missing checkpoint is an error, like in the reference")
     p.add_argument("--steps_per_epoch", default=50, type=int)
     p.add_argument("--val_refs", default=64, type=int)
+    p.add_argument("--lanes", default=3, type=int,
+                   help="validate.py: refs in flight on independent CUDA streams (batch-1 inference is latency bound)")
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = forward-only parity mode (validate/demo)")
     p.add_argument("--no_graph", action="store_true", help="do not capture the step in a CUDA graph")
     return p

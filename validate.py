@@ -40,6 +40,49 @@ def synthetic_refs(args, n, rank=0, world=1, sentences=2, orig=(480, 640)):
         yield idx, img, ids.t().unsqueeze(0).contiguous(), target
 
 
+def _prefetch(gen, depth=8):
+    """Run the (CPU) ref generator in a background thread and hand out PINNED tensors, so that the .cuda(non_blocking=True) copies
+    of the loop are asynchronous and the next refs are produced while the current one is being launched."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    end = object()
+
+    def work():
+        try:
+            for idx, img, ids, target in gen:
+                q.put((idx, img.pin_memory(), ids.pin_memory(), target.pin_memory()))
+        finally:
+            q.put(end)
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        yield item
+
+
+class _Lanes:
+    """K refs in flight: each lane owns a Stage1Inference (its own CUDA graphs and static buffers) and a stream.  At batch 1 a
+    ref is a chain of ~700 latency-bound kernels that occupy a few SMs each, so independent refs overlap almost perfectly."""
+
+    def __init__(self, k, make):
+        self.main = torch.cuda.current_stream()
+        self.lanes = [(make(), torch.cuda.Stream()) for _ in range(max(1, k))]
+        for _, st in self.lanes:
+            st.wait_stream(self.main)
+        self.i = 0
+
+    def next(self):
+        lane = self.lanes[self.i % len(self.lanes)]
+        self.i += 1
+        return lane
+
+    def join(self):
+        for _, st in self.lanes:
+            self.main.wait_stream(st)
+
+
 def _to_original(cam, size):
     from tris_b200 import ops
     return ops.resize_bilinear_ac(cam.contiguous(), size[0], size[1])
@@ -59,22 +102,30 @@ def validate(args, refs, model, local_rank=0):
     host reads the per-map statistics once at the end instead of three times per sentence."""
     from tris_b200 import ops
     from tris_b200.infer import AsyncCamWriter, Stage1Inference
-    inf = Stage1Inference(model, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
-    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
+    graphs = not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16"
     stats = torch.zeros((max(1, args.val_refs) * 8, 4), device="cuda")
+    model.eval().engine().ensure_fresh()
+    torch.cuda.synchronize()                  # derived operands (side-stream weight packs) complete before any lane starts
+    lanes = _Lanes(getattr(args, "lanes", 1) if graphs else 1, lambda: Stage1Inference(model, use_graphs=graphs))
+    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
     n = 0
     for idx, img, word_ids, target in refs:
-        img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
-        c4 = inf.features(img)                                  # once per ref
-        for j in range(word_ids.shape[-1]):
-            out = inf.respond(c4, word_ids[:, :, j].contiguous(), tuple(img.shape[2:]))
-            cam = _to_original(out, target.shape[-2:])
-            if n >= stats.shape[0]:
-                stats = torch.cat([stats, torch.zeros_like(stats)])
-            cam_n, _ = ops.cam_metrics(cam, target[0], stats=stats[n])
-            n += 1
-            if writer is not None:
-                writer.submit(f"{idx}_{j}", cam_n)
+        inf, st = lanes.next()
+        with torch.cuda.stream(st):
+            img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
+            c4 = inf.features(img)                                  # once per ref
+            for j in range(word_ids.shape[-1]):
+                out = inf.respond(c4, word_ids[:, :, j].contiguous(), tuple(img.shape[2:]))
+                cam = _to_original(out, target.shape[-2:])
+                if n >= stats.shape[0]:
+                    lanes.join()
+                    stats = torch.cat([stats, torch.zeros_like(stats)])
+                    torch.cuda.synchronize()
+                cam_n, _ = ops.cam_metrics(cam, target[0], stats=stats[n])
+                n += 1
+                if writer is not None:
+                    writer.submit(f"{idx}_{j}", cam_n)
+    lanes.join()
     if writer is not None:
         writer.close()
     return _finish(stats, n)
@@ -87,25 +138,34 @@ def validate_same_sentence(args, refs, model, aux, local_rank=0):
     (tris_prms_select), the resize and the metrics (tris_cam_metrics) never leave the device."""
     from tris_b200 import ops
     from tris_b200.infer import AsyncCamWriter, Stage1Inference
-    inf = Stage1Inference(model, aux, use_graphs=not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16")
-    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
+    graphs = not getattr(args, "no_graph", False) and getattr(args, "precision", "bf16") == "bf16"
     stats = torch.zeros((max(1, args.val_refs), 4), device="cuda")
+    model.eval().engine().ensure_fresh()
+    aux._engine().ensure_fresh()
+    torch.cuda.synchronize()                  # derived operands (side-stream weight packs) complete before any lane starts
+    lanes = _Lanes(getattr(args, "lanes", 1) if graphs else 1, lambda: Stage1Inference(model, aux, use_graphs=graphs))
+    writer = AsyncCamWriter(args.cam_save_dir) if (args.save_cam and args.cam_save_dir) else None
     names, n = [], 0
     for idx, img, word_ids, target in refs:
-        img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
-        S = word_ids.shape[-1]
-        ids = word_ids[0].t().contiguous()                                     # [S, L]
-        c4 = inf.features(img)
-        cams = torch.cat([inf.respond(c4, ids[j:j + 1], tuple(img.shape[2:])).clone() for j in range(S)])   # [S,1,H,W]
-        f, g = inf.prms_features(cams, img, ids)
-        best, _ = ops.prms_select(f, g)                                         # device-side arg-max of the summed get_scores
-        big = _to_original(cams, target.shape[-2:])                             # [S,1,oH,oW]
-        if n >= stats.shape[0]:
-            stats = torch.cat([stats, torch.zeros_like(stats)])
-        cam_n, _ = ops.cam_metrics(big, target[0], sel=best, stats=stats[n])
-        n += 1
-        if writer is not None:
-            writer.submit(f"{idx}_{idx}", cam_n)                                 # {idx}_{img_id}.npy, written in the background
+        inf, st = lanes.next()
+        with torch.cuda.stream(st):
+            img, word_ids, target = img.cuda(non_blocking=True), word_ids.cuda(non_blocking=True), target.cuda(non_blocking=True)
+            S = word_ids.shape[-1]
+            ids = word_ids[0].t().contiguous()                                     # [S, L]
+            c4 = inf.features(img)
+            cams = torch.cat([inf.respond(c4, ids[j:j + 1], tuple(img.shape[2:])).clone() for j in range(S)])   # [S,1,H,W]
+            f, g = inf.prms_features(cams, img, ids)
+            best, _ = ops.prms_select(f, g)                                         # device-side arg-max of the summed get_scores
+            big = _to_original(cams, target.shape[-2:])                             # [S,1,oH,oW]
+            if n >= stats.shape[0]:
+                lanes.join()
+                stats = torch.cat([stats, torch.zeros_like(stats)])
+                torch.cuda.synchronize()
+            cam_n, _ = ops.cam_metrics(big, target[0], sel=best, stats=stats[n])
+            n += 1
+            if writer is not None:
+                writer.submit(f"{idx}_{idx}", cam_n)                                 # {idx}_{img_id}.npy, written in the background
+    lanes.join()
     if writer is not None:
         names = writer.close()
     if args.save_cam and args.name_save_dir:
@@ -128,7 +188,7 @@ def main(args):
     if args.pretrain:
         ck = torch.load(args.pretrain, map_location="cpu")
         print("load:", model.load_state_dict(ck.get("model", ck), strict=False))
-    refs = synthetic_refs(args, args.val_refs, rank, world)
+    refs = _prefetch(synthetic_refs(args, args.val_refs, rank, world))
     t0 = time.time()
     if args.prms:
         aux, _ = clip.load("ViT-B/32", device="cuda", jit=False, txt_length=args.max_query_len,
