@@ -156,3 +156,21 @@ def test_average_of_rank_gradients_equals_big_batch_mean():
         per_rank.append(g)
     (g_all,) = torch.autograd.grad(torch.tanh(torch.cat(xs) @ w).mean(), w)
     assert torch.allclose((per_rank[0] + per_rank[1]) * 0.5, g_all, atol=1e-6)
+
+
+def test_cam_writer_npy_bytes_match_numpy_save(tmp_path):
+    """validate.py --save_cam writes `{idx}_{img_id}.npy` with three raw system calls (header once per shape + payload): the file
+    must be byte-identical to what the reference's np.save produces (validate.py:354-359), for the shapes / dtypes it dumps."""
+    import os
+    import numpy as np
+    from tris_b200.infer import npy_header
+    for shape, dt in (((480, 640), np.float32), ((1, 1, 320, 320), np.float32), ((7,), np.float64)):
+        a = np.random.default_rng(0).random(shape).astype(dt)
+        p1, p2 = str(tmp_path / "a.npy"), str(tmp_path / "b.npy")
+        np.save(p1, a)
+        fd = os.open(p2, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.write(fd, npy_header(a))
+        os.write(fd, memoryview(a).cast("B"))
+        os.close(fd)
+        assert open(p1, "rb").read() == open(p2, "rb").read()
+        assert np.array_equal(np.load(p2), a)

@@ -86,6 +86,15 @@ class Stage1Inference:
         return f, g
 
 
+def npy_header(arr) -> bytes:
+    """.npy v1.0 header of a numpy array: header + the raw C-order bytes is byte-identical to np.save (tests/test_host_cpu.py)."""
+    import io
+    from numpy.lib import format as npf
+    b = io.BytesIO()
+    npf.write_array_header_1_0(b, npf.header_data_from_array_1_0(arr))
+    return b.getvalue()
+
+
 class AsyncCamWriter:
     """Background `.npy` writer for the PRMS / CAM dump (validate.py:354-359, file name `{idx}_{img_id}.npy`, consumed by the
     IRNet stage): the map is copied to pinned host memory on a copy stream and written by a worker thread, so that disk I/O
@@ -122,12 +131,7 @@ class AsyncCamWriter:
     def _header(self, key, host):
         """.npy v1.0 header bytes for this shape / dtype (identical for every map of a run: built once)."""
         if key not in self._hdr:
-            import io
-            import numpy as np
-            from numpy.lib import format as npf
-            b = io.BytesIO()
-            npf.write_array_header_1_0(b, npf.header_data_from_array_1_0(host.numpy()))
-            self._hdr[key] = b.getvalue()
+            self._hdr[key] = npy_header(host.numpy())
         return self._hdr[key]
 
     def submit(self, name, cam):
