@@ -29,6 +29,9 @@ class _Rec:
 
 @pytest.fixture(scope="module")
 def ref():
+    from baseline import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no copy of the reference sources (baseline/_ref is made by __graft_entry__.build() where /root/reference exists)")
     from baseline import ref_step as RS
     ns, args = RS.load(batch=8)
     return RS, ns, args
