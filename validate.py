@@ -47,17 +47,22 @@ def _prefetch(gen, depth=8):
     import threading
     q = queue.Queue(maxsize=depth)
     end = object()
+    failure = []
 
     def work():
         try:
             for idx, img, ids, target in gen:
                 q.put((idx, img.pin_memory(), ids.pin_memory(), target.pin_memory()))
+        except BaseException as e:      # re-raised in the consumer: a failing loader must not look like an empty one
+            failure.append(e)
         finally:
             q.put(end)
     threading.Thread(target=work, daemon=True).start()
     while True:
         item = q.get()
         if item is end:
+            if failure:
+                raise failure[0]
             return
         yield item
 
